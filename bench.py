@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the render_rays hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision MODE] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- a 400x400 lego-shape frame, 160 000
+synthetic camera rays, N_samples=64 + N_importance=64, 8x256 MLP, fp32-parity arithmetic,
+seeded default-init weights.  One step = one complete render_rays of the frame.
+N > 1 (torchrun, one rank per GPU): weak scaling -- the job is N frames, each rank renders its
+contiguous 160 000-ray slab and the rendered pixels (16 B/ray) are all-gathered over NCCL.
+
+value  : rays/s, inputs resident in HBM, CUDA-event timed per step (L2 flushed between steps,
+         outside the event pairs), max over ranks.
+e2e    : same metric through the public API with HOST (pinned) rays: H2D of the rays and D2H
+         of [rgb_fine, depth_fine] inside the timed region.
+roofline: the fine-pass field kernel (2/3 of all FLOPs) timed alone with CUDA events.
+cpu_baseline: the CPU oracle port (the reference is Python/torch; it cannot travel to the GPU
+         box) on the host cores, on a bounded sample of the same rays.
+--impl reference: only the CPU arm, same JSON schema, "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOP_PER_POINT = 2 * 593408          # SURVEY.md 8d (full head)
+N_SAMPLES, N_IMPORTANCE = 64, 64
+POINTS_PER_RAY = N_SAMPLES + (N_SAMPLES + N_IMPORTANCE)
+METRIC = "rays/sec (64c+64f samples, 8x256 MLP)"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            d["_source"] = "measured"
+            return d
+        except Exception:
+            pass
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_sm = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.samples.append((sm, reasons, util))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=1)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0}
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        loaded = [s for s in self.samples if s[2] >= 50] or self.samples
+        seen = set()
+        for _, r, _ in loaded:
+            for k, bit in names.items():
+                if r & bit:
+                    seen.add(k)
+        return {"sm_mhz": statistics.median(s[0] for s in loaded), "sm_max_mhz": self.max_sm,
+                "reasons": sorted(seen), "samples": len(loaded)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_oracle_rate(rays_cpu, n_sample, repeats=1, budget_s=25.0):
+    """rays/s of the CPU oracle port (oracle/render_oracle.py) on the first n_sample rays."""
+    from oracle import render_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    pc, pf = orc.default_init_params(0), orc.default_init_params(1)
+    r = rays_cpu[:n_sample].contiguous()
+    best, t_total, done = None, 0.0, 0
+    with torch.no_grad():
+        orc.render_rays(pc, pf, r[:256], N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, noise_std=0.0,
+                        white_back=True)
+        while done < repeats and (done == 0 or t_total < budget_s):
+            t0 = time.perf_counter()
+            orc.render_rays(pc, pf, r, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, noise_std=0.0,
+                            white_back=True)
+            dt = time.perf_counter() - t0
+            t_total += dt
+            done += 1
+            best = dt if best is None else min(best, dt)
+    return r.shape[0] / best, torch.get_num_threads(), best
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's algorithm on the host CPU (oracle port: the reference is
+    a Python package with missing deps (kornia, pytorch_lightning) that cannot travel to the GPU box)."""
+    if rank != 0:
+        return
+    from sinnerf_b200 import synthetic
+    rays = synthetic.frame_rays("lego", seed=0)
+    n_sample = 4096
+    for _ in range(max(0, args.warmup)):
+        cpu_oracle_rate(rays, 512)
+    times = []
+    for _ in range(args.steps):
+        rate, cores, dt = cpu_oracle_rate(rays, n_sample)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = n_sample / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args.gpus, "cpu-oracle"),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"first {n_sample} rays of the 400x400 frame per step, torch CPU fp32, "
+                                   f"{cores} threads"},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, precision):
+    return {"workload": "configs[1]: 400x400 lego-shape frame, 160000 rays/GPU, N_samples=64 N_importance=64, "
+                        "8x256 MLP (use_new_activation), perturb=0 noise_std=0 white_back, seeded default-init weights",
+            "rays_per_step_per_gpu": 160000, "global_rays_per_step": 160000 * n_gpus, "precision": precision,
+            "parallelism": f"ray-sharded x{n_gpus} + NCCL all-gather of pixels" if n_gpus > 1 else "single GPU",
+            "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA-event pairs)"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("SINNERF_B200_BENCH_PRECISION", "auto"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from sinnerf_b200 import _lib, synthetic
+    from sinnerf_b200 import build as _build
+    from sinnerf_b200.distributed import pack_pixels
+    from sinnerf_b200.nerf import NeRF, Embedding
+    from sinnerf_b200 import rendering
+    from oracle.render_oracle import default_init_params  # weights only (seeded init), not on the timed path
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.load()
+    precision = args.precision
+    if precision == "auto":
+        precision = "f16x3" if lib.snb_packed_weights_bytes(_lib.PRECISIONS["f16x3"]) > 0 else "fp32"
+    prec_id = _lib.precision_id(precision)
+
+    models = []
+    for seed in (0, 1):
+        m = NeRF(use_new_activation=True)
+        m.load_state_dict(default_init_params(seed))
+        models.append(m.to(dev))
+    emb = [Embedding(3, 10), Embedding(3, 4)]
+    rays_cpu = synthetic.frame_rays("lego", seed=rank)          # this rank's frame (weak scaling)
+    n = rays_cpu.shape[0]
+    rays_pinned = rays_cpu.pin_memory()
+    rays_dev = rays_cpu.to(dev)
+    pix_host = torch.empty(n, 4).pin_memory()
+    gathered = torch.empty(n * world, 4, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rendering.DRAW_UNUSED_NOISE = True     # keep the reference's randn draws (rendering.py:224)
+
+    def step(r):
+        with torch.no_grad():
+            res = rendering.render_rays(models, emb, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, True,
+                                        precision=precision)
+        pix = pack_pixels(res)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pix)
+        return pix
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, k):
+        """k steps, each bracketed by its own event pair; L2 flushed between steps."""
+        evs = []
+        sync_all()
+        for _ in range(k):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        sync_all()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    for _ in range(max(3, args.warmup)):
+        step(rays_dev)
+    sync_all()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    total_ms = timed(lambda: step(rays_dev), args.steps)
+
+    def e2e_step():
+        r = rays_pinned.to(dev, non_blocking=True)
+        pix = step(r)
+        pix_host.copy_(pix, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timed(e2e_step, args.steps)
+    # ---- dominant kernel alone: the fine-pass field kernel (128 samples/ray)
+    S_f = N_SAMPLES + N_IMPORTANCE
+    with torch.no_grad():
+        inter = rendering.render_rays(models, emb, rays_dev, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, True,
+                                      precision=precision, _return_intermediates=True)["_inter"]
+    z_f, raw_f = inter["z_fine"], inter["raw_fine"]
+    img_f = models[1].packed_weights(prec_id)
+
+    def field_only():
+        _lib.check(lib.snb_field_forward(_lib.ptr(img_f), prec_id, _lib.ptr(rays_dev), _lib.ptr(z_f), n, S_f, 0,
+                                         _lib.ptr(raw_f), _lib.stream_ptr(dev)), "snb_field_forward")
+
+    for _ in range(2):
+        field_only()
+    kern_ms = timed(field_only, max(3, min(args.steps, 10))) / max(3, min(args.steps, 10))
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peaks = load_peaks()
+        ms_per_step = total_ms / args.steps
+        value = n * world / (ms_per_step / 1e3)
+        e2e_value = n * world / ((e2e_ms / args.steps) / 1e3)
+        kern_tflops = FLOP_PER_POINT * n * S_f / (kern_ms / 1e3) / 1e12
+        tensor_peak = peaks.get("bf16_tflops_sustained" if kern_ms > 50 else "bf16_tflops")
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "field_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(precision)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": {"fp32": "fp32 (FFMA)", "f16x3": "fp32-parity: fp16 hi/lo split x3 on tcgen05, fp32 accumulate",
+                      "bf16x3": "bf16 hi/lo split x3 on tcgen05, fp32 accumulate",
+                      "bf16": "bf16 operands, fp32 accumulate"}[precision],
+            "data": "synthetic",
+            "config": workload_config(world, precision),
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 32 * world,
+                    "d2h_bytes_per_step": n * 16 * world, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": 6 * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "fine-pass field kernel (160000 rays x 128 samples)",
+                         "achieved": kern_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
+                         "frac": kern_tflops / tensor_peak if tensor_peak else None, "traffic": traffic,
+                         "peak_source": f"MEASURED_PEAKS.json ({peaks['_source']}), dense bf16 cuBLAS",
+                         "ms_per_launch": kern_ms,
+                         "flops": "algorithmic 2*593408 per point (SURVEY 8d); "
+                                  + ("executed MMA flops are 3x (hi*hi + hi*lo + lo*hi)" if precision.endswith("x3")
+                                     else "FFMA pipe, not tensor cores" if precision == "fp32" else "single pass")},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            rate, cores, dt = cpu_oracle_rate(rays_cpu, 8192)
+            line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
+                                    "sample": f"first 8192 rays of the same frame, one pass ({dt:.1f} s), "
+                                              f"oracle/render_oracle.py on torch CPU fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

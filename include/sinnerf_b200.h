@@ -1,0 +1,164 @@
+/* sinnerf_b200.h -- C ABI of libsinnerf_b200.so
+ *
+ * Drop-in boundary for the SinNeRF volumetric-rendering hot path.  The reference
+ * (VITA-Group/SinNeRF @ bf147e4) is pure Python/PyTorch and has no FFI of its own; the
+ * "operator interface" this library sits behind is
+ *     models/rendering.py:126-139   render_rays(models, embeddings, rays, ...)
+ *     models/rendering.py:15-61     sample_pdf(bins, weights, N_importance, det, eps)
+ *     models/nerf.py:24-41          Embedding.forward
+ *     models/nerf.py:105-148        NeRF.forward(x, sigma_only)
+ * Each entry point below names the reference lines it replaces.  The Python mirror of
+ * that interface (sinnerf_b200/rendering.py, sinnerf_b200/nerf.py) binds these symbols
+ * with ctypes; INTEGRATION.md shows the two import lines a maintainer changes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to caller-owned memory unless marked "host";
+ *    the library never allocates, frees or retains device memory;
+ *  - tensors are dense row-major fp32 unless a stride argument is given;
+ *  - `stream` is a cudaStream_t / CUstream passed as void*; all work is enqueued on it,
+ *    nothing synchronises the host;
+ *  - functions return SNB_OK (0) or a negative SNB_ERR_* code; snb_last_error() returns
+ *    a thread-local message for the last failing call on this thread;
+ *  - the library is sm_100a only; snb_device_check() reports anything else as an error.
+ */
+#ifndef SINNERF_B200_H
+#define SINNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNB_VERSION 100 /* 0.1.0 */
+
+#define SNB_OK 0
+#define SNB_ERR_INVALID (-1)     /* bad argument (shape, null pointer, alignment)       */
+#define SNB_ERR_CUDA (-2)        /* a CUDA runtime call or launch failed                */
+#define SNB_ERR_UNSUPPORTED (-3) /* architecture / field shape / precision not built    */
+
+/* Arithmetic used for the field MLP (every other stage is always fp32).
+ *  FP32     : FFMA on CUDA cores, fp32 accumulate            -- exact-fp32 mode
+ *  F16X3    : tcgen05 kind::f16, operands split hi+lo (fp16), 3 products, fp32 accumulate
+ *             in TMEM -- meets the <=1e-4 fp32 parity bar on tensor cores
+ *  BF16X3   : same with bf16 halves (wider range, ~2e-5)
+ *  BF16     : single-pass bf16 operands, fp32 accumulate (BASELINE.json configs[2])
+ */
+#define SNB_PREC_FP32 0
+#define SNB_PREC_F16X3 1
+#define SNB_PREC_BF16X3 2
+#define SNB_PREC_BF16 3
+
+/* Field MLP shape: NeRF(D=8, W=256, in_channels_xyz=63, in_channels_dir=27, skips=[4])
+ * (models/nerf.py:47-50), the only shape SinNeRF instantiates (models/sinnerf.py:137,140).
+ * Parameter pointer order for snb_pack_weights = the module's state_dict order:
+ *   xyz_encoding_{1..8}.0.{weight,bias}, xyz_encoding_final.{weight,bias},
+ *   dir_encoding.0.{weight,bias}, sigma.{weight,bias}, rgb.0.{weight,bias}    (24 tensors)
+ * weights are nn.Linear layout (out, in) row-major fp32. */
+#define SNB_N_PARAM_TENSORS 24
+#define SNB_XYZ_FREQS 10
+#define SNB_DIR_FREQS 4
+#define SNB_XYZ_CH 63
+#define SNB_DIR_CH 27
+
+int snb_version(void);
+const char* snb_last_error(void);
+/* SNB_OK iff the current CUDA device is compute capability 10.x; fills SM count. */
+int snb_device_check(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- weights --------------------------------------------------------------------- */
+/* Bytes of the packed weight image for a precision mode (device buffer the caller owns). */
+size_t snb_packed_weights_bytes(int precision);
+/* Re-layout the 24 nn.Linear tensors into the image the field kernels stream
+ * (K-major, padded 63->64 / 27->32, skip and dir concatenations split; hi/lo halves for
+ * the split modes).  `params` is a HOST array of 24 device pointers.
+ * new_activation: 1 = ShiftedSoftplus/WidenedSigmoid (models/activations.py:8-35),
+ *                 0 = ReLU/Sigmoid (models/nerf.py:92-103); stored in the image header. */
+int snb_pack_weights(const float* const* params, int precision, int new_activation, void* packed,
+                     void* stream);
+
+/* ---- stages (each maps to one oracle function) ------------------------------------- */
+
+/* models/rendering.py:264-282.  rays (N,8) [o,d,near,far]; z_steps (S,) = torch.linspace(0,1,S);
+ * perturb_u (N,S) U[0,1) or NULL when perturb == 0.  -> z_vals (N,S). */
+int snb_sample_coarse(const float* rays, const float* z_steps, const float* perturb_u, float perturb,
+                      int use_disp, int64_t n_rays, int n_samples, float* z_vals, void* stream);
+
+/* Embedding.forward, models/nerf.py:24-41 (logscale bands 2^k).  x (B,C) -> out (B, C*(2L+1)). */
+int snb_embed(const float* x, int64_t n, int in_channels, int n_freqs, float* out, void* stream);
+
+/* NeRF.forward, models/nerf.py:105-148, on already-embedded rows.
+ * x (P, 63+27) (or (P,63) with row stride x_stride when sigma_only) -> out (P,4) [r,g,b,sigma]
+ * or (P,1). */
+int snb_mlp_forward(const void* packed, int precision, const float* x, int64_t x_stride, int64_t n_points,
+                    int sigma_only, float* out, void* stream);
+
+/* The fused field pass, models/rendering.py:184-212 + :284-285: points o+d*z, xyz and dir
+ * embeddings, MLP -- no (P,63)/(P,27)/(P,256) tensor ever reaches HBM.
+ * -> raw (N,S,4), or sigma (N,S) when sigma_only. */
+int snb_field_forward(const void* packed, int precision, const float* rays, const float* z_vals,
+                      int64_t n_rays, int n_samples, int sigma_only, float* raw, void* stream);
+
+/* models/rendering.py:215-248.  raw (N,S,4) (raw_channels=4) or sigma (N,S) (raw_channels=1);
+ * noise (N,S) standard-normal draws or NULL (treated as 0; the reference scales by noise_std).
+ * rgb (N,3) / depth (N,) may be NULL with raw_channels==1 (weights_only branch :237-238). */
+int snb_composite_forward(const float* raw, int raw_channels, const float* z_vals, const float* rays,
+                          const float* noise, float noise_std, int white_back, int64_t n_rays,
+                          int n_samples, float* rgb, float* depth, float* weights, void* stream);
+
+/* sample_pdf, models/rendering.py:15-61.  bins (N,M+1) row stride bins_stride; weights (N,M) row
+ * stride w_stride; u: det -> (n_importance,) = torch.linspace(0,1,n_importance) with u_stride 0,
+ * else (N,n_importance) with u_stride n_importance.  -> samples (N,n_importance). */
+int snb_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride,
+                   const float* u, int64_t u_stride, int64_t n_rays, int m, int n_importance, float eps,
+                   float* samples, void* stream);
+
+/* models/rendering.py:310-315 in one kernel: z_mid, sample_pdf over weights[:,1:-1], then the
+ * sorted union with the coarse depths.  -> z_fine (N,S+Ni); z_new (N,Ni) optional (may be NULL). */
+int snb_importance_merge(const float* z_coarse, const float* weights_coarse, const float* u,
+                         int64_t u_stride, int64_t n_rays, int n_samples, int n_importance, float eps,
+                         float* z_fine, float* z_new, void* stream);
+
+/* ---- whole path -------------------------------------------------------------------- */
+typedef struct SnbRenderArgs {
+  const float* rays;        /* (N,8)                                                    */
+  int64_t n_rays;
+  int n_samples;            /* N_samples                                                */
+  int n_importance;         /* N_importance (0 = coarse only)                           */
+  int use_disp;
+  float perturb;
+  float noise_std;
+  int white_back;
+  int test_time;            /* coarse pass sigma-only (rendering.py:287-292)            */
+  int precision;            /* SNB_PREC_*                                               */
+  const void* packed_coarse;
+  const void* packed_fine;  /* NULL iff n_importance == 0                               */
+  const float* z_steps;     /* (S,)  torch.linspace(0,1,S)                              */
+  const float* u_steps;     /* (Ni,) torch.linspace(0,1,Ni), used when perturb == 0     */
+  /* random draws in the reference's order; NULL = not used             */
+  const float* perturb_u;   /* (N,S)   rand,  needed iff perturb > 0                    */
+  const float* noise_coarse;/* (N,S)   randn, read iff noise_std != 0                   */
+  const float* pdf_u;       /* (N,Ni)  rand,  needed iff perturb > 0 and Ni > 0         */
+  const float* noise_fine;  /* (N,S+Ni) randn                                           */
+  /* outputs                                                                            */
+  float* z_coarse;          /* (N,S)      workspace + output                            */
+  float* raw_coarse;        /* (N,S,4) or (N,S) when test_time -- workspace             */
+  float* rgb_coarse;        /* (N,3)   NULL when test_time                              */
+  float* depth_coarse;      /* (N,)    NULL when test_time                              */
+  float* weights_coarse;    /* (N,S)                                                    */
+  float* z_fine;            /* (N,S+Ni)                                                 */
+  float* raw_fine;          /* (N,S+Ni,4) workspace                                     */
+  float* rgb_fine;          /* (N,3)                                                    */
+  float* depth_fine;        /* (N,)                                                     */
+  float* weights_fine;      /* (N,S+Ni)                                                 */
+} SnbRenderArgs;
+
+/* render_rays forward, models/rendering.py:126-335, as one call: every stage above enqueued
+ * back to back on `stream`. */
+int snb_render_forward(const SnbRenderArgs* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SINNERF_B200_H */

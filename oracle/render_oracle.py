@@ -87,7 +87,7 @@ def field_mlp(p: Params, xyz_enc: Tensor, dir_enc: Optional[Tensor],
     for i in range(depth):
         if i in skips:
             h = torch.cat([xyz_enc, h], dim=-1)
-        h = torch.relu(_affine(p, f"xyz_encoding_{i + 1}.0", h))
+        h = torch.relu_(_affine(p, f"xyz_encoding_{i + 1}.0", h))  # nn.ReLU(True), nerf.py:73
     sigma = _affine(p, "sigma", h)
     if sigma_only:
         return sigma
@@ -188,7 +188,7 @@ def sample_pdf(bins: Tensor, weights: Tensor, n_importance: int, det: bool = Fal
 # --------------------------------------------------------------------------- #
 def field_pass(p: Params, rays_o: Tensor, rays_d: Tensor, dir_enc: Tensor, z: Tensor,
                noise: Optional[Tensor], white_back: bool, weights_only: bool = False,
-               new_activation: bool = True, point_chunk: int = 1 << 16):
+               new_activation: bool = True, point_chunk: int = 1 << 15):
     """models/rendering.py:161-248 (the nested ``inference``) incl. the point
     generation at :284-285 / :317-318.  Returns a dict with raw (N,S,4) (or
     sigma (N,S)), rgb, depth, weights.

@@ -1,0 +1,17 @@
+"""Process-wide settings of the sm_100a path."""
+import os
+
+_precision = os.environ.get("SINNERF_B200_PRECISION", "fp32")
+
+
+def set_precision(name: str) -> None:
+    """Arithmetic of the field MLP: 'fp32' (FFMA, exact), 'f16x3' / 'bf16x3' (tcgen05, split operands,
+    fp32-parity), 'bf16' (tcgen05 single pass).  Everything outside the MLP is always fp32."""
+    from . import _lib
+    _lib.precision_id(name)
+    global _precision
+    _precision = name
+
+
+def get_precision() -> str:
+    return _precision

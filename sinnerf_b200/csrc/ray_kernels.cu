@@ -1,0 +1,409 @@
+// ray_kernels.cu -- the HBM-bound per-ray stages of render_rays as warp-level kernels:
+//   sample_coarse   models/rendering.py:264-282   (stratified depths)
+//   embed           models/nerf.py:24-41          (stand-alone Embedding.forward)
+//   composite_fwd   models/rendering.py:215-248   (sigma -> alpha -> transmittance -> rgb/depth)
+//   sample_pdf      models/rendering.py:15-61     (inverse-CDF sampling)
+//   importance_merge models/rendering.py:310-315  (z_mid + sample_pdf + sorted union)
+// Mapping: one warp per ray, samples strided over lanes, shuffles for the scans.
+// All of these are bound by HBM traffic; algorithmic bytes are listed per kernel.
+#include "common.cuh"
+
+namespace snb {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------
+// sample_coarse: 32 B/ray in, 4*S B/ray out (+4*S in for perturb_u)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float z_at(float near, float far, float t, int use_disp) {
+  // near*(1-t) + far*t with every product and sum rounded separately, as torch evaluates it
+  const float omt = __fsub_rn(1.0f, t);
+  if (!use_disp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
+  const float a = __fmul_rn(__fdiv_rn(1.0f, near), omt);
+  const float b = __fmul_rn(__fdiv_rn(1.0f, far), t);
+  return __fdiv_rn(1.0f, __fadd_rn(a, b));
+}
+
+__global__ void sample_coarse_kernel(const float* __restrict__ rays, const float* __restrict__ z_steps,
+                                     const float* __restrict__ perturb_u, float perturb, int use_disp,
+                                     long long n_rays, int S, float* __restrict__ z_out) {
+  const long long total = n_rays * S;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long ray = e / S;
+    const int i = (int)(e - ray * S);
+    const float near = rays[ray * 8 + 6], far = rays[ray * 8 + 7];
+    float z = z_at(near, far, z_steps[i], use_disp);
+    if (perturb > 0.f) {
+      // rendering.py:274-282: lower=[z0, mid...], upper=[mid..., z_last]
+      const float zl = i > 0 ? z_at(near, far, z_steps[i - 1], use_disp) : z;
+      const float zr = i < S - 1 ? z_at(near, far, z_steps[i + 1], use_disp) : z;
+      const float lower = i > 0 ? __fmul_rn(0.5f, __fadd_rn(zl, z)) : z;
+      const float upper = i < S - 1 ? __fmul_rn(0.5f, __fadd_rn(z, zr)) : z;
+      const float pr = __fmul_rn(perturb, perturb_u[e]);
+      z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), pr));
+    }
+    z_out[e] = z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// embed: 4*C B in, 4*C*(2L+1) B out per row (264 B/point for C=3, L=10).
+// A block computes 128 rows into smem (one sincosf per (row, freq, channel)), then streams
+// the dense [128][C*(2L+1)] tile out with 128-bit stores.
+// ---------------------------------------------------------------------------------------
+constexpr int kEmbedRows = 128;
+__global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x, long long n, int C, int L,
+                                                    float* __restrict__ out) {
+  extern __shared__ float tile[];  // [kEmbedRows][W]
+  const int W = C * (2 * L + 1);
+  const long long nblocks = (n + kEmbedRows - 1) / kEmbedRows;
+  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const long long r0 = blk * kEmbedRows;
+    const int rows = (int)((n - r0) < kEmbedRows ? (n - r0) : kEmbedRows);
+    const int items = rows * C * (L + 1);
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int r = it / (C * (L + 1));
+      const int rem = it - r * (C * (L + 1));
+      const int f = rem / C, c = rem - f * C;  // f == 0: identity block; f >= 1: frequency f-1
+      const float v = x[(r0 + r) * C + c];
+      if (f == 0) {
+        tile[r * W + c] = v;
+      } else {
+        float sn, cs;
+        sincosf(v * (float)(1 << (f - 1)), &sn, &cs);
+        tile[r * W + C + (f - 1) * 2 * C + c] = sn;
+        tile[r * W + C + (f - 1) * 2 * C + C + c] = cs;
+      }
+    }
+    __syncthreads();
+    const long long base = r0 * W;  // float offset; 128*W*4 B per block keeps 16-B alignment
+    const int nflt = rows * W;
+    if ((base & 3) == 0) {
+      const int nvec = nflt >> 2;
+      float4* o4 = reinterpret_cast<float4*>(out + base);
+      const float4* t4 = reinterpret_cast<const float4*>(tile);
+      for (int v = threadIdx.x; v < nvec; v += blockDim.x) o4[v] = t4[v];
+      for (int v = (nvec << 2) + threadIdx.x; v < nflt; v += blockDim.x) out[base + v] = tile[v];
+    } else {
+      for (int v = threadIdx.x; v < nflt; v += blockDim.x) out[base + v] = tile[v];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// composite_fwd: read 16 B (rgb sigma) + 4 B (z) [+4 B noise] per point, write 4 B (w) per
+// point, + 32 B in (ray) and 16 B out (rgb, depth) per ray  ->  24 B/point + 48 B/ray.
+// One warp per ray; 32 samples per step; inclusive product scan by shuffles, carried across
+// steps; the exclusive product is the scan shifted by one lane.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) composite_fwd_kernel(
+    const float* __restrict__ raw, int raw_channels, const float* __restrict__ z_vals,
+    const float* __restrict__ rays, const float* __restrict__ noise, float noise_std, int white_back,
+    long long n_rays, int S, float* __restrict__ rgb_out, float* __restrict__ depth_out,
+    float* __restrict__ w_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long ray = warp; ray < n_rays; ray += nwarps) {
+    const float dx = rays[ray * 8 + 3], dy = rays[ray * 8 + 4], dz = rays[ray * 8 + 5];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.norm(dir_, dim=-1)
+    const float* zr = z_vals + ray * S;
+    float carry = 1.0f;  // product of (1 - alpha + 1e-10) over all earlier samples
+    float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aw = 0.f;
+    for (int base = 0; base < S; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < S;
+      float sigma = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, z = 0.f, delta = 0.f;
+      if (valid) {
+        if (raw_channels == 4) {
+          const float4 v = reinterpret_cast<const float4*>(raw)[ray * S + i];
+          cr = v.x; cg = v.y; cb = v.z; sigma = v.w;
+        } else {
+          sigma = raw[ray * S + i];
+        }
+        z = zr[i];
+        delta = (i + 1 < S) ? __fsub_rn(zr[i + 1], z) : 1e10f;
+        delta = __fmul_rn(delta, dnorm);
+        if (noise != nullptr) sigma = __fadd_rn(sigma, __fmul_rn(noise[ray * S + i], noise_std));
+      }
+      // alpha = 1 - exp(-delta * relu(sigma))
+      const float alpha = valid ? __fsub_rn(1.0f, expf(-__fmul_rn(delta, fmaxf(sigma, 0.f)))) : 0.f;
+      const float t = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+      float scan = t;  // inclusive product scan over the 32 lanes
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const float up = __shfl_up_sync(kFull, scan, off);
+        if (lane >= off) scan *= up;
+      }
+      float excl = __shfl_up_sync(kFull, scan, 1);
+      if (lane == 0) excl = 1.0f;
+      const float T = carry * excl;
+      const float w = alpha * T;
+      carry *= __shfl_sync(kFull, scan, 31);
+      if (valid) {
+        w_out[ray * S + i] = w;
+        ar = fmaf(w, cr, ar); ag = fmaf(w, cg, ag); ab = fmaf(w, cb, ab);
+        ad = fmaf(w, z, ad);
+        aw += w;
+      }
+    }
+    if (rgb_out != nullptr || depth_out != nullptr) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        ar += __shfl_xor_sync(kFull, ar, off);
+        ag += __shfl_xor_sync(kFull, ag, off);
+        ab += __shfl_xor_sync(kFull, ab, off);
+        ad += __shfl_xor_sync(kFull, ad, off);
+        aw += __shfl_xor_sync(kFull, aw, off);
+      }
+      if (lane == 0) {
+        if (rgb_out != nullptr) {
+          if (white_back) {  // rgb + 1 - weights_sum  (rendering.py:245-246)
+            ar = __fsub_rn(__fadd_rn(ar, 1.0f), aw);
+            ag = __fsub_rn(__fadd_rn(ag, 1.0f), aw);
+            ab = __fsub_rn(__fadd_rn(ab, 1.0f), aw);
+          }
+          rgb_out[ray * 3 + 0] = ar; rgb_out[ray * 3 + 1] = ag; rgb_out[ray * 3 + 2] = ab;
+        }
+        if (depth_out != nullptr) depth_out[ray] = ad;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// inverse-CDF sampling.  One warp per ray; cdf (M+1 floats) and, for the merged variant, the
+// S+Ni depths live in the warp's slice of shared memory.
+//   sample_pdf:       in 4*(M + M+1) B/ray (+4*Ni u), out 4*Ni B/ray
+//   importance_merge: in 8*S B/ray (z, w), out 4*(S+Ni) B/ray
+// ---------------------------------------------------------------------------------------
+// Build cdf[0..M] in smem from weights w[0..M-1] (row pointer), eps as in rendering.py:29-36.
+__device__ __forceinline__ void warp_build_cdf(const float* __restrict__ w, int M, float eps, float* cdf,
+                                               int lane) {
+  float sum = 0.f;
+  for (int i = lane; i < M; i += 32) sum += __fadd_rn(w[i], eps);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(kFull, sum, off);
+  float carry = 0.f;
+  if (lane == 0) cdf[0] = 0.f;
+  for (int base = 0; base < M; base += 32) {
+    const int i = base + lane;
+    float v = i < M ? __fdiv_rn(__fadd_rn(w[i], eps), sum) : 0.f;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const float up = __shfl_up_sync(kFull, v, off);
+      if (lane >= off) v += up;
+    }
+    if (i < M) cdf[i + 1] = carry + v;
+    carry += __shfl_sync(kFull, v, 31);
+  }
+  __syncwarp();
+}
+
+// One inverse-CDF sample.  bin(j) returns bins[j].  rendering.py:46-61.
+template <class BinFn>
+__device__ __forceinline__ float invert_cdf(const float* cdf, int M, float u, float eps, BinFn bin) {
+  // idx = #{ j in [0,M] : cdf[j] <= u }   (searchsorted right=True)
+  int lo = 0, hi = M + 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  const int below = lo - 1 < 0 ? 0 : lo - 1;
+  const int above = lo > M ? M : lo;
+  const float c0 = cdf[below], c1 = cdf[above];
+  const float b0 = bin(below), b1 = bin(above);
+  float denom = __fsub_rn(c1, c0);
+  if (denom < eps) denom = 1.0f;
+  // bins_g0 + (u - cdf_g0) / denom * (bins_g1 - bins_g0)
+  return __fadd_rn(b0, __fmul_rn(__fdiv_rn(__fsub_rn(u, c0), denom), __fsub_rn(b1, b0)));
+}
+
+__global__ void __launch_bounds__(128) sample_pdf_kernel(
+    const float* __restrict__ bins, long long bins_stride, const float* __restrict__ weights,
+    long long w_stride, const float* __restrict__ u, long long u_stride, long long n_rays, int M, int Ni,
+    float eps, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* cdf = sm + wib * (M + 1);
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long ray = warp; ray < n_rays; ray += nwarps) {
+    warp_build_cdf(weights + ray * w_stride, M, eps, cdf, lane);
+    const float* b = bins + ray * bins_stride;
+    for (int j = lane; j < Ni; j += 32) {
+      const float uj = u[ray * u_stride + j];
+      out[ray * Ni + j] = invert_cdf(cdf, M, uj, eps, [&](int k) { return b[k]; });
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(128) importance_merge_kernel(
+    const float* __restrict__ z_coarse, const float* __restrict__ w_coarse, const float* __restrict__ u,
+    long long u_stride, long long n_rays, int S, int Ni, float eps, float* __restrict__ z_fine,
+    float* __restrict__ z_new_out) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int M = S - 2, F = S + Ni;
+  const int per_warp = (S - 1) + F;   // cdf (M+1 = S-1) + merged depths
+  float* cdf = sm + wib * per_warp;
+  float* zs = cdf + (S - 1);
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long ray = warp; ray < n_rays; ray += nwarps) {
+    const float* zc = z_coarse + ray * S;
+    for (int i = lane; i < S; i += 32) zs[i] = zc[i];
+    warp_build_cdf(w_coarse + ray * S + 1, M, eps, cdf, lane);  // weights[:, 1:-1]
+    for (int j = lane; j < Ni; j += 32) {
+      const float uj = u[ray * u_stride + j];
+      // bins = z_mid = 0.5*(z[k] + z[k+1])   (rendering.py:310)
+      const float zn = invert_cdf(cdf, M, uj, eps,
+                                  [&](int k) { return __fmul_rn(0.5f, __fadd_rn(zs[k], zs[k + 1])); });
+      zs[S + j] = zn;
+      if (z_new_out != nullptr) z_new_out[ray * Ni + j] = zn;
+    }
+    __syncwarp();
+    // sorted union (torch.sort(cat([z, z_new]))): rank of every element among all F
+    for (int i = lane; i < F; i += 32) {
+      const float v = zs[i];
+      int rank = 0;
+      for (int k = 0; k < F; ++k) {
+        const float o = zs[k];
+        rank += (o < v) || (o == v && k < i);
+      }
+      z_fine[ray * F + rank] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// weight packing (fp32 image)
+// ---------------------------------------------------------------------------------------
+struct ParamPtrs {
+  const float* p[SNB_N_PARAM_TENSORS];
+};
+
+__global__ void pack_fp32_kernel(ParamPtrs pp, int new_activation, unsigned char* image) {
+  constexpr Fp32Layout L = make_fp32_layout();
+  PackedHeader* hdr = reinterpret_cast<PackedHeader*>(image);
+  float* W = reinterpret_cast<float*>(image + sizeof(PackedHeader));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hdr->magic = kMagic;
+    hdr->precision = SNB_PREC_FP32;
+    hdr->new_activation = new_activation;
+  }
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < L.total; e += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (e < L.b[0]) {
+      int l = 0;
+      while (l + 1 < kNumGemm && e >= L.w[l + 1]) ++l;
+      const int rel = e - L.w[l];
+      const int N = gemm_n(l);
+      const int k = rel / N, n = rel - k * N;
+      const int col = gemm_src_col(l, k);
+      const int src_k = l == 0 ? 63 : (l == 4 ? 319 : (l == 9 ? 283 : 256));
+      if (col >= 0) v = pp.p[param_weight_index(l)][n * src_k + col];
+    } else if (e < L.sigma_w) {
+      int l = 0;
+      while (l + 1 < kNumGemm && e >= L.b[l + 1]) ++l;
+      v = pp.p[param_weight_index(l) + 1][e - L.b[l]];
+    } else if (e < L.sigma_b) {
+      v = pp.p[kSigmaW][e - L.sigma_w];
+    } else if (e < L.rgb_w) {
+      v = (e == L.sigma_b) ? pp.p[kSigmaB][0] : 0.f;
+    } else if (e < L.rgb_b) {
+      v = pp.p[kRgbW][e - L.rgb_w];
+    } else {
+      v = (e - L.rgb_b < 3) ? pp.p[kRgbB][e - L.rgb_b] : 0.f;
+    }
+    W[e] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------
+static int grid_for(long long work_items, int per_block, int cap_blocks) {
+  long long b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  return (int)(b < cap_blocks ? b : cap_blocks);
+}
+static int device_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+int launch_sample_coarse(const float* rays, const float* z_steps, const float* perturb_u, float perturb,
+                         int use_disp, int64_t n_rays, int S, float* z, cudaStream_t st) {
+  if (n_rays == 0) return SNB_OK;
+  const int grid = grid_for(n_rays * S, 256, device_sms() * 8);
+  sample_coarse_kernel<<<grid, 256, 0, st>>>(rays, z_steps, perturb_u, perturb, use_disp, n_rays, S, z);
+  return check_launch("sample_coarse_kernel");
+}
+
+int launch_embed(const float* x, int64_t n, int C, int L, float* out, cudaStream_t st) {
+  if (n == 0) return SNB_OK;
+  const size_t smem = (size_t)kEmbedRows * C * (2 * L + 1) * sizeof(float);
+  if (smem > 200 * 1024) return fail(SNB_ERR_UNSUPPORTED, "snb_embed: C*(2L+1) too large for the smem tile");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(embed): %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  const int grid = grid_for(n, kEmbedRows, device_sms() * 4);
+  embed_kernel<<<grid, 256, smem, st>>>(x, n, C, L, out);
+  return check_launch("embed_kernel");
+}
+
+int launch_composite(const float* raw, int raw_channels, const float* z, const float* rays, const float* noise,
+                     float noise_std, int white_back, int64_t n_rays, int S, float* rgb, float* depth,
+                     float* w, cudaStream_t st) {
+  if (n_rays == 0) return SNB_OK;
+  const int grid = grid_for(n_rays, 8, device_sms() * 8);
+  composite_fwd_kernel<<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays,
+                                             S, rgb, depth, w);
+  return check_launch("composite_fwd_kernel");
+}
+
+int launch_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride,
+                      const float* u, int64_t u_stride, int64_t n_rays, int M, int Ni, float eps, float* out,
+                      cudaStream_t st) {
+  if (n_rays == 0) return SNB_OK;
+  const size_t smem = (size_t)4 * (M + 1) * sizeof(float);
+  if (smem > 48 * 1024) return fail(SNB_ERR_UNSUPPORTED, "snb_sample_pdf: too many bins (%d)", M);
+  const int grid = grid_for(n_rays, 4, device_sms() * 16);
+  sample_pdf_kernel<<<grid, 128, smem, st>>>(bins, bins_stride, weights, w_stride, u, u_stride, n_rays, M, Ni,
+                                             eps, out);
+  return check_launch("sample_pdf_kernel");
+}
+
+int launch_importance_merge(const float* z_coarse, const float* w_coarse, const float* u, int64_t u_stride,
+                            int64_t n_rays, int S, int Ni, float eps, float* z_fine, float* z_new,
+                            cudaStream_t st) {
+  if (n_rays == 0) return SNB_OK;
+  const size_t smem = (size_t)4 * ((S - 1) + (S + Ni)) * sizeof(float);
+  if (smem > 48 * 1024) return fail(SNB_ERR_UNSUPPORTED, "snb_importance_merge: S+Ni too large");
+  const int grid = grid_for(n_rays, 4, device_sms() * 16);
+  importance_merge_kernel<<<grid, 128, smem, st>>>(z_coarse, w_coarse, u, u_stride, n_rays, S, Ni, eps, z_fine,
+                                                   z_new);
+  return check_launch("importance_merge_kernel");
+}
+
+int launch_pack_fp32(const float* const* params, int new_activation, void* image, cudaStream_t st) {
+  ParamPtrs pp;
+  for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i) pp.p[i] = params[i];
+  pack_fp32_kernel<<<device_sms() * 2, 256, 0, st>>>(pp, new_activation, reinterpret_cast<unsigned char*>(image));
+  return check_launch("pack_fp32_kernel");
+}
+
+}  // namespace snb

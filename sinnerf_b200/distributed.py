@@ -1,0 +1,47 @@
+"""Ray-sharded rendering over one process per GPU (torch.distributed, NCCL over NVLink).
+
+Rays are independent (every reduction in render_rays runs along the sample axis of one ray),
+so a frame shards into contiguous ray slabs with no data-path collective; the only exchange is
+an all-gather of the rendered pixels, 16 B/ray ([r, g, b, depth] of the fine pass).  The
+reference has no equivalent (its eval.py is single-GPU, eval.py:141-142); training keeps the
+reference's scheme: torch DDP gradient all-reduce around the unchanged Lightning module.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous slab [lo, hi) of rank `rank`: ceil(n / world) rays each, the tail ranks may be
+    short or empty (same rule as the reference's own ray-chunk loop, eval.py:92-94)."""
+    per = -(-n // world_size) if n > 0 else 0
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def pack_pixels(result: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """(n,4) slab [rgb_fine, depth_fine] -- what a frame consumer needs (eval.py:161-169)."""
+    return torch.cat([result["rgb_fine"], result["depth_fine"].unsqueeze(-1)], dim=-1).contiguous()
+
+
+def render_rays_sharded(render_fn: Callable[[torch.Tensor], Dict[str, torch.Tensor]], rays: torch.Tensor,
+                        group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Render this rank's slab of `rays` (the same (N,8) tensor on every rank) with `render_fn`
+    and all-gather the pixels.  Returns (N,4) [r,g,b,depth] on every rank, bitwise independent
+    of the world size.  One collective: all_gather_into_tensor of equal (padded) slabs."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = rays.shape[0]
+    lo, hi = shard_bounds(n, world, rank)
+    per = -(-n // world) if n > 0 else 0
+    local = pack_pixels(render_fn(rays[lo:hi])) if hi > lo else rays.new_zeros((0, 4))
+    if world == 1:
+        return local
+    if local.shape[0] < per:  # pad the short tail slab so the collective is uniform
+        local = torch.cat([local, local.new_zeros((per - local.shape[0], 4))], dim=0)
+    out = local.new_empty((per * world, 4))
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out[:n]

@@ -1,0 +1,152 @@
+"""`Embedding` and `NeRF` with the reference's constructor signatures, attributes and state-dict
+(reference models/nerf.py:7-41, :46-148), executing on libsinnerf_b200's sm_100a kernels.
+
+The modules are parameter containers: `nn.Linear` leaves with the reference's names
+(`xyz_encoding_{1..8}.0.{weight,bias}`, `xyz_encoding_final.*`, `dir_encoding.0.*`, `sigma.*`,
+`rgb.0.*`) so `utils.load_ckpt`, optimizers, DDP and Lightning checkpoints keep working
+(reference utils/__init__.py:60-83, train.py:25-30).  `forward` never runs the nn.Linear
+modules; it calls the fused CUDA kernels through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib
+from . import config
+
+
+class ShiftedSoftplus(nn.Module):
+    """Marker for reference models/activations.py:54-71; evaluated inside the fused kernels."""
+
+    def forward(self, x):  # pragma: no cover - never on the hot path
+        raise RuntimeError("activation is fused into the sm_100a field kernel; call NeRF.forward")
+
+
+class WidenedSigmoid(ShiftedSoftplus):
+    """Marker for reference models/activations.py:38-51."""
+
+
+class Embedding(nn.Module):
+    def __init__(self, in_channels, N_freqs, logscale=True):
+        """Embeds x to (x, sin(2^k x), cos(2^k x), ...)  -- reference models/nerf.py:8-22."""
+        super().__init__()
+        self.N_freqs = N_freqs
+        self.in_channels = in_channels
+        self.funcs = [torch.sin, torch.cos]
+        self.out_channels = in_channels * (len(self.funcs) * N_freqs + 1)
+        if logscale:
+            self.freq_bands = 2 ** torch.linspace(0, N_freqs - 1, N_freqs)
+        else:
+            self.freq_bands = torch.linspace(1, 2 ** (N_freqs - 1), N_freqs)
+        self._logscale = bool(logscale)
+
+    def forward(self, x):
+        """x (B, in_channels) -> (B, out_channels)  -- reference models/nerf.py:24-41."""
+        if not self._logscale:
+            raise NotImplementedError("sinnerf_b200.Embedding: only logscale=True bands (the ones SinNeRF "
+                                      "uses, models/sinnerf.py:131-132) have a kernel")
+        _lib.require_device(x, "Embedding.forward")
+        if x.dim() != 2 or x.shape[1] != self.in_channels:
+            raise ValueError(f"Embedding.forward: expected (B, {self.in_channels}), got {tuple(x.shape)}")
+        xc = x.detach().to(torch.float32).contiguous()
+        out = torch.empty(xc.shape[0], self.out_channels, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().snb_embed(_lib.ptr(xc), xc.shape[0], self.in_channels, self.N_freqs,
+                                             _lib.ptr(out), _lib.stream_ptr(x.device)), "snb_embed")
+        return out
+
+
+class NeRF(nn.Module):
+    def __init__(self, D=8, W=256, in_channels_xyz=63, in_channels_dir=27, skips=[4], use_new_activation=False):
+        """Same arguments and parameter names as reference models/nerf.py:47-103."""
+        super().__init__()
+        self.D, self.W = D, W
+        self.in_channels_xyz, self.in_channels_dir = in_channels_xyz, in_channels_dir
+        self.skips = skips
+        self.use_new_activation = bool(use_new_activation)
+        for i in range(D):
+            if i == 0:
+                layer = nn.Linear(in_channels_xyz, W)
+            elif i in skips:
+                layer = nn.Linear(W + in_channels_xyz, W)
+            else:
+                layer = nn.Linear(W, W)
+            setattr(self, f"xyz_encoding_{i + 1}", nn.Sequential(layer, nn.ReLU(True)))
+        self.xyz_encoding_final = nn.Linear(W, W)
+        if use_new_activation:
+            self.dir_encoding = nn.Sequential(nn.Linear(W + in_channels_dir, W // 2), ShiftedSoftplus())
+            self.sigma = nn.Linear(W, 1)
+            self.rgb = nn.Sequential(nn.Linear(W // 2, 3), WidenedSigmoid())
+        else:
+            self.dir_encoding = nn.Sequential(nn.Linear(W + in_channels_dir, W // 2), nn.ReLU(True))
+            self.sigma = nn.Linear(W, 1)
+            self.rgb = nn.Sequential(nn.Linear(W // 2, 3), nn.Sigmoid())
+        self._packed = {}  # precision id -> (key, uint8 device tensor)
+
+    # ------------------------------------------------------------------ kernels' weight image
+    def _check_shape(self):
+        if (self.D, self.W, self.in_channels_xyz, self.in_channels_dir, list(self.skips)) != (8, 256, 63, 27, [4]):
+            raise NotImplementedError(
+                "sinnerf_b200 kernels are specialised for NeRF(D=8, W=256, in_channels_xyz=63, "
+                "in_channels_dir=27, skips=[4]) -- the shape SinNeRF instantiates (models/sinnerf.py:137,140)")
+
+    def _param_list(self):
+        ps = []
+        for i in range(self.D):
+            lin = getattr(self, f"xyz_encoding_{i + 1}")[0]
+            ps += [lin.weight, lin.bias]
+        ps += [self.xyz_encoding_final.weight, self.xyz_encoding_final.bias,
+               self.dir_encoding[0].weight, self.dir_encoding[0].bias,
+               self.sigma.weight, self.sigma.bias, self.rgb[0].weight, self.rgb[0].bias]
+        return ps
+
+    def packed_weights(self, precision=None) -> torch.Tensor:
+        """Device image of the weights in the layout the kernels stream (C ABI snb_pack_weights).
+        Cached; rebuilt when any parameter was modified in place (optimizer step, load_state_dict)
+        or moved."""
+        self._check_shape()
+        prec = _lib.precision_id(config.get_precision() if precision is None else precision)
+        ps = self._param_list()
+        dev = ps[0].device
+        _lib.require_device(ps[0], "NeRF")
+        key = (str(dev),) + tuple((p.data_ptr(), p._version) for p in ps)
+        hit = self._packed.get(prec)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        lib = _lib.load()
+        nbytes = lib.snb_packed_weights_bytes(prec)
+        if nbytes == 0:
+            raise NotImplementedError(f"precision mode {prec} is not available in this build")
+        image = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        srcs = []
+        for p in ps:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("NeRF parameters must be fp32 tensors on one CUDA device")
+            srcs.append(p.detach().contiguous())
+        arr = (C.c_void_p * len(srcs))(*[s.data_ptr() for s in srcs])
+        with torch.cuda.device(dev):
+            _lib.check(lib.snb_pack_weights(arr, prec, int(self.use_new_activation), _lib.ptr(image),
+                                            _lib.stream_ptr(dev)), "snb_pack_weights")
+        self._packed[prec] = (key, image)
+        return image
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, sigma_only=False):
+        """x (B, 63(+27)) embedded position (and direction) -> (B,4) [rgb, sigma], or (B,1) sigma
+        -- reference models/nerf.py:105-148."""
+        _lib.require_device(x, "NeRF.forward")
+        need = self.in_channels_xyz if sigma_only else self.in_channels_xyz + self.in_channels_dir
+        if x.dim() != 2 or x.shape[1] != need:
+            raise ValueError(f"NeRF.forward: expected (B, {need}), got {tuple(x.shape)}")
+        prec = _lib.precision_id(config.get_precision())
+        image = self.packed_weights(prec)
+        xc = x.detach().to(torch.float32).contiguous()
+        out = torch.empty(xc.shape[0], 1 if sigma_only else 4, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().snb_mlp_forward(_lib.ptr(image), prec, _lib.ptr(xc), xc.shape[1], xc.shape[0],
+                                                   int(bool(sigma_only)), _lib.ptr(out),
+                                                   _lib.stream_ptr(x.device)), "snb_mlp_forward")
+        return out
