@@ -113,10 +113,38 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
+_best_threads = None
+
+
+def pick_threads(rays_cpu):
+    """torch CPU GEMMs of this size stop scaling (and regress) long before 128 threads: try a few
+    thread counts on a 256-ray sample and keep the fastest -- 'all the threads it can use'."""
+    global _best_threads
+    if _best_threads is None:
+        from oracle import render_oracle as orc
+        pc, pf = orc.default_init_params(0), orc.default_init_params(1)
+        ncpu = os.cpu_count() or 1
+        best = None
+        for nt in sorted({ncpu, max(1, ncpu // 2), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}):
+            torch.set_num_threads(nt)
+            r = rays_cpu[:256].contiguous()
+            with torch.no_grad():
+                orc.render_rays(pc, pf, r[:64], N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, noise_std=0.0,
+                                white_back=True)
+                t0 = time.perf_counter()
+                orc.render_rays(pc, pf, r, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, noise_std=0.0,
+                                white_back=True)
+                dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, nt)
+        _best_threads = best[1]
+    return _best_threads
+
+
 def cpu_oracle_rate(rays_cpu, n_sample, repeats=1, budget_s=25.0):
     """rays/s of the CPU oracle port (oracle/render_oracle.py) on the first n_sample rays."""
     from oracle import render_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(pick_threads(rays_cpu))
     pc, pf = orc.default_init_params(0), orc.default_init_params(1)
     r = rays_cpu[:n_sample].contiguous()
     best, t_total, done = None, 0.0, 0
@@ -141,7 +169,7 @@ def run_reference_arm(args, rank, world):
         return
     from sinnerf_b200 import synthetic
     rays = synthetic.frame_rays("lego", seed=0)
-    n_sample = 4096
+    n_sample = 2048
     for _ in range(max(0, args.warmup)):
         cpu_oracle_rate(rays, 512)
     times = []
@@ -332,9 +360,9 @@ def main():
                                      else "FFMA pipe, not tensor cores" if precision == "fp32" else "single pass")},
         }
         if not args.no_cpu_baseline and world == 1:
-            rate, cores, dt = cpu_oracle_rate(rays_cpu, 8192)
+            rate, cores, dt = cpu_oracle_rate(rays_cpu, 2048)
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": f"first 8192 rays of the same frame, one pass ({dt:.1f} s), "
+                                    "sample": f"first 2048 rays of the same frame, one pass ({dt:.1f} s), "
                                               f"oracle/render_oracle.py on torch CPU fp32"}
         print(json.dumps(line), flush=True)
     if world > 1:

