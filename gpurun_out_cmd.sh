@@ -1,6 +1,7 @@
 mkdir -p gpurun_out
-echo "=== probe" ; timeout 120 ./probes/umma_probe > gpurun_out/probe.log 2>&1; echo "probe rc=$?" >> gpurun_out/probe.log; cat gpurun_out/probe.log
-echo "=== pytest fp32"; SINNERF_B200_TEST_MODES=fp32 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_fp32.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_fp32.log; tail -15 gpurun_out/pytest_fp32.log
-echo "=== pytest tc mlp"; SINNERF_B200_TEST_MODES=f16x3,bf16x3,bf16 timeout 300 python -m pytest tests -m gpu -q -k "mlp_forward" > gpurun_out/pytest_tc_mlp.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_tc_mlp.log; tail -25 gpurun_out/pytest_tc_mlp.log
-echo "=== pytest tc all"; SINNERF_B200_TEST_MODES=f16x3,bf16x3,bf16 timeout 600 python -m pytest tests -m gpu -q > gpurun_out/pytest_tc.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_tc.log; tail -25 gpurun_out/pytest_tc.log
-echo "=== bench f16x3"; timeout 300 python bench.py --steps 5 --warmup 3 --precision f16x3 > gpurun_out/bench_f16x3.json 2> gpurun_out/bench_f16x3.err; tail -c 2500 gpurun_out/bench_f16x3.json; tail -3 gpurun_out/bench_f16x3.err
+echo "=== pytest all modes (cluster 2)"; timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
+echo "=== pytest cluster 4 (mlp + render)"; SNB_TC_CLUSTER=4 timeout 600 python -m pytest tests -m gpu -q -x -k "mlp_forward or render_rays_vs" > gpurun_out/pytest_gpu_c4.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu_c4.log; tail -3 gpurun_out/pytest_gpu_c4.log
+echo "=== timing"
+for c in 1 2 4; do for d in 0 6; do SNB_TC_CLUSTER=$c SNB_TC_DEBUG=$d timeout 120 python tools/time_field.py --precision f16x3 --iters 3 2>&1 | tail -1 | sed "s/^/cluster=$c /"; done; done | tee gpurun_out/timing_cluster.log
+for c in 2 4; do SNB_TC_CLUSTER=$c timeout 120 python tools/time_field.py --precision bf16 --iters 3 2>&1 | tail -1 | sed "s/^/cluster=$c /"; done | tee -a gpurun_out/timing_cluster.log
+for c in 2 4; do SNB_TC_CLUSTER=$c SNB_TC_DEBUG=2 timeout 120 python tools/time_field.py --precision f16x3 --iters 3 2>&1 | tail -1 | sed "s/^/cluster=$c /"; done | tee -a gpurun_out/timing_cluster.log

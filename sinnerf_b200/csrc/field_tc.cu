@@ -173,6 +173,35 @@ __device__ __forceinline__ void split16(float x, uint16_t& hi, uint16_t& lo) {
   lo = cvt16<kBf16>(x - up16<kBf16>(hi));
 }
 
+// Two values at once, with the packed converts (F2FP.*.PACK_AB, full-rate pipe) instead of four
+// scalar F2F (quarter-rate MIO pipe): hi = pack(x0, x1); lo = pack(x0 - up(hi.x), x1 - up(hi.y)).
+template <bool kBf16, bool kSplit>
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  if (kBf16) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    if (kSplit) {
+      const float b0 = __uint_as_float(hi << 16), b1 = __uint_as_float(hi & 0xffff0000u);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - b0, x1 - b1);
+      lo = *reinterpret_cast<const uint32_t*>(&l);
+    } else {
+      lo = 0;
+    }
+  } else {
+    x0 = fminf(fmaxf(x0, -65504.f), 65504.f);
+    x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    if (kSplit) {
+      const float2 b = __half22float2(h);
+      const __half2 l = __floats2half2_rn(x0 - b.x, x1 - b.y);
+      lo = *reinterpret_cast<const uint32_t*>(&l);
+    } else {
+      lo = 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ pack kernel
 struct ParamPtrsTc {
   const float* p[SNB_N_PARAM_TENSORS];
@@ -271,7 +300,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 // canonical (SWIZZLE_NONE, K-major) byte offset of element (row, k) in a [k8][128 rows][8] block
 __device__ __forceinline__ uint32_t canon_off(int row, int k) { return (uint32_t)(k >> 3) * (kTile * 16) + row * 16 + (k & 7) * 2; }
 
-template <bool kBf16, bool kSplit, bool kEmbedded>
+template <bool kBf16, bool kSplit, bool kEmbedded, int kCluster>
 __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   using Smem = TcSmem<kSplit>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -285,13 +314,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   const float* g_cst = reinterpret_cast<const float*>(p.image + sizeof(PackedHeader));
   const unsigned char* g_chunks = p.image + sizeof(PackedHeader) + kConstBytes;
   const long long ntiles = (p.n_points + kTile - 1) / kTile;
+  // every CTA runs the same number of tile slots (the weight ring is shared cluster-wide, so the
+  // CTAs of a cluster advance in lock step); slots past the end compute on zeros and store nothing
+  const long long tile_end = ((ntiles + gridDim.x - 1) / gridDim.x) * gridDim.x;
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1);
+  const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
   const int n_layers_epi = p.sigma_only ? 8 : 9;   // layers with a TMEM->TMEM epilogue
   const int n_chunks = p.sigma_only ? c_chunks.n_sigma_only : c_chunks.n_total;
 
   // ---------------- one-time setup
   for (int i = tid; i < kConstFloats; i += kThreads) s.cst[i] = g_cst[i];
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], kCluster); }
     mbar_init(&s.d_full[0], 1); mbar_init(&s.d_full[1], 1);
     mbar_init(&s.a_ready[0], kEpiWarps * 32); mbar_init(&s.a_ready[1], kEpiWarps * 32);
     mbar_init(&s.enc_ready, kEpiWarps * 32);
@@ -300,74 +334,92 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   if (warp == kMmaWarp) tmem_alloc<512>(&s.tmem_base);
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tbase = s.tmem_base;
 
   if (warp == kLoadWarp) {
-    // ======================= weight loader (one thread) =======================
-    if (lane == 0) {
+    // ======================= weight loader (one elected lane) =======================
+    if (elect_one()) {
       uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         for (int ci = 0; ci < n_chunks; ++ci, ++it) {
           const uint32_t st = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(&s.empty[st], ph ^ 1);
           if ((p.debug & 1) && it >= kStages) { mbar_arrive(&s.full[st]); continue; }
           mbar_arrive_expect_tx(&s.full[st], kChunkBytes);
-          bulk_g2s(s.ring[st], g_chunks + (size_t)ci * kChunkBytes, kChunkBytes, &s.full[st]);
+          if (kCluster == 1) {
+            bulk_g2s(s.ring[st], g_chunks + (size_t)ci * kChunkBytes, kChunkBytes, &s.full[st]);
+          } else {
+            // this CTA fetches its 1/kCluster slice of the chunk once from L2 and multicasts it
+            constexpr uint32_t kSlice = kChunkBytes / kCluster;
+            bulk_g2s_multicast(s.ring[st] + cta_rank * kSlice, g_chunks + (size_t)ci * kChunkBytes + cta_rank * kSlice,
+                               kSlice, &s.full[st], kClusterMask);
+          }
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ======================= MMA issuer (one thread) =======================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(kBf16 ? kFmtBF16 : kFmtF16, kTile, kNh);
-      const uint32_t enc_hi = smem_u32(s.enc[0]), dir_hi = smem_u32(s.dir[0]);
-      const uint32_t enc_lo = smem_u32(s.enc[kSplit ? 1 : 0]), dir_lo = smem_u32(s.dir[kSplit ? 1 : 0]);
-      uint32_t it = 0, ph_a[2] = {0, 0}, ph_enc = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int ci = 0; ci < n_chunks; ++ci, ++it) {
-          const Chunk c = c_chunks.c[ci];
-          if (c.wait == WAIT_ENC) { mbar_wait(&s.enc_ready, ph_enc); ph_enc ^= 1; }
-          else if (c.wait == WAIT_A0) { mbar_wait(&s.a_ready[0], ph_a[0]); ph_a[0] ^= 1; }
-          else if (c.wait == WAIT_A1) { mbar_wait(&s.a_ready[1], ph_a[1]); ph_a[1] ^= 1; }
-          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(&s.full[st], ph);
-          tc_fence_after();
+    // ======================= MMA issuer =======================
+    // The whole warp walks the chunk schedule (uniform control flow); one elected lane issues
+    // the tcgen05 instructions of a chunk, so they compile to single uniform-datapath ops.
+    const uint32_t idesc = make_idesc(kBf16 ? kFmtBF16 : kFmtF16, kTile, kNh);
+    const uint32_t enc_hi = smem_u32(s.enc[0]), dir_hi = smem_u32(s.dir[0]);
+    const uint32_t enc_lo = smem_u32(s.enc[kSplit ? 1 : 0]), dir_lo = smem_u32(s.dir[kSplit ? 1 : 0]);
+    const uint32_t ring0 = smem_u32(s.ring[0]);
+    // descriptor templates: only the 14-bit start-address field changes between MMAs
+    const uint64_t desc_b0 = make_smem_desc(0, kNh * 16, 128);
+    const uint64_t desc_a0 = make_smem_desc(0, kTile * 16, 128);
+    constexpr uint32_t kStepB = (2 * kNh * 16) >> 4;     // one K16 step inside a chunk, in 16-B units
+    constexpr uint32_t kStepA = (2 * kTile * 16) >> 4;
+    uint32_t it = 0, ph_a0 = 0, ph_a1 = 0, ph_enc = 0;
+    for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      for (int ci = 0; ci < n_chunks; ++ci, ++it) {
+        const Chunk c = c_chunks.c[ci];
+        if (c.wait == WAIT_ENC) { mbar_wait(&s.enc_ready, ph_enc); ph_enc ^= 1; }
+        else if (c.wait == WAIT_A0) { mbar_wait(&s.a_ready[0], ph_a0); ph_a0 ^= 1; }
+        else if (c.wait == WAIT_A1) { mbar_wait(&s.a_ready[1], ph_a1); ph_a1 ^= 1; }
+        const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(&s.full[st], ph);
+        tc_fence_after();
+        if (elect_one() && !(p.debug & 4)) {
           const uint32_t d = tbase + kColD + (c.layer == 9 ? 0 : c.half * kNh);
-          const uint32_t w_hi = smem_u32(s.ring[st]);
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            if (p.debug & 4) break;
-            const uint64_t b_hi = make_smem_desc(w_hi + ks * 2 * (kNh * 16), kNh * 16, 128);
-            const uint64_t b_lo = make_smem_desc(w_hi + kLoOff + ks * 2 * (kNh * 16), kNh * 16, 128);
-            const uint32_t acc0 = !(c.first && ks == 0);
-            if (c.src == SRC_HID) {
-              const uint32_t kcol = (uint32_t)(c.kc * kKc + ks * 16) >> 1;
-              mma_ts(d, tbase + kColAhi + kcol, b_hi, idesc, acc0);
-              if (kSplit) {
-                mma_ts(d, tbase + kColAlo + kcol, b_hi, idesc, 1);
-                mma_ts(d, tbase + kColAhi + kcol, b_lo, idesc, 1);
-              }
-            } else {
-              const uint32_t a_off = (uint32_t)(c.kc * 4 + ks * 2) * (kTile * 16);
-              const uint32_t ahi = (c.src == SRC_ENC ? enc_hi : dir_hi) + a_off;
-              const uint32_t alo = (c.src == SRC_ENC ? enc_lo : dir_lo) + a_off;
-              mma_ss(d, make_smem_desc(ahi, kTile * 16, 128), b_hi, idesc, acc0);
-              if (kSplit) {
-                mma_ss(d, make_smem_desc(alo, kTile * 16, 128), b_hi, idesc, 1);
-                mma_ss(d, make_smem_desc(ahi, kTile * 16, 128), b_lo, idesc, 1);
-              }
-            }
+          const uint64_t b_hi = desc_b0 + ((ring0 + st * kChunkBytes) >> 4);
+          const uint64_t b_lo = b_hi + (kLoOff >> 4);
+          const uint32_t acc0 = c.first ? 0u : 1u;
+          if (c.src == SRC_HID) {
+            const uint32_t a_hi = tbase + kColAhi + ((uint32_t)(c.kc * kKc) >> 1);
+            const uint32_t a_lo = tbase + kColAlo + ((uint32_t)(c.kc * kKc) >> 1);
+            mma_ts(d, a_hi, b_hi, idesc, acc0);
+            if (kSplit) { mma_ts(d, a_lo, b_hi, idesc, 1); mma_ts(d, a_hi, b_lo, idesc, 1); }
+            mma_ts(d, a_hi + 8, b_hi + kStepB, idesc, 1);
+            if (kSplit) { mma_ts(d, a_lo + 8, b_hi + kStepB, idesc, 1); mma_ts(d, a_hi + 8, b_lo + kStepB, idesc, 1); }
+          } else {
+            const uint32_t a_off = (uint32_t)(c.kc * 4) * (kTile * 16);
+            const uint64_t a_hi = desc_a0 + (((c.src == SRC_ENC ? enc_hi : dir_hi) + a_off) >> 4);
+            const uint64_t a_lo = desc_a0 + (((c.src == SRC_ENC ? enc_lo : dir_lo) + a_off) >> 4);
+            mma_ss(d, a_hi, b_hi, idesc, acc0);
+            if (kSplit) { mma_ss(d, a_lo, b_hi, idesc, 1); mma_ss(d, a_hi, b_lo, idesc, 1); }
+            mma_ss(d, a_hi + kStepA, b_hi + kStepB, idesc, 1);
+            if (kSplit) { mma_ss(d, a_lo + kStepA, b_hi + kStepB, idesc, 1); mma_ss(d, a_hi + kStepA, b_lo + kStepB, idesc, 1); }
           }
-          mma_commit(&s.empty[st]);                       // ring slot free once these MMAs retire
+          // ring slot free (in every CTA of the cluster) once these MMAs retire
+          if (kCluster == 1) mma_commit(&s.empty[st]); else mma_commit_multicast(&s.empty[st], kClusterMask);
           if (c.commit == COMMIT_D0) mma_commit(&s.d_full[0]);
           else if (c.commit == COMMIT_D1) mma_commit(&s.d_full[1]);
+        } else if (p.debug & 4) {
+          if (elect_one()) {
+            if (kCluster == 1) mma_commit(&s.empty[st]); else mma_commit_multicast(&s.empty[st], kClusterMask);
+            if (c.commit == COMMIT_D0) mma_commit(&s.d_full[0]);
+            else if (c.commit == COMMIT_D1) mma_commit(&s.d_full[1]);
+          }
         }
-        if (p.sigma_only) {
-          // layer 8's epilogue arrives on a_ready[0..1] with nobody waiting: consume the phases
-          mbar_wait(&s.a_ready[0], ph_a[0]); ph_a[0] ^= 1;
-          mbar_wait(&s.a_ready[1], ph_a[1]); ph_a[1] ^= 1;
-        }
+        __syncwarp();
+      }
+      if (p.sigma_only) {
+        // layer 8's epilogue arrives on a_ready[0..1] with nobody waiting: consume the phases
+        mbar_wait(&s.a_ready[0], ph_a0); ph_a0 ^= 1;
+        mbar_wait(&s.a_ready[1], ph_a1); ph_a1 ^= 1;
       }
     }
   } else {
@@ -376,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     uint32_t ph_d[2] = {0, 0};
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
       const long long p0 = tile * kTile;
       const long long pt = p0 + row;
       // ---------------- prologue: positional encodings -> smem (canonical, hi/lo)
@@ -467,11 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
                 sig_part = fmaf(x0, s.cst[CL.sigma_w + c0 + j], sig_part);
                 sig_part = fmaf(x1, s.cst[CL.sigma_w + c0 + j + 1], sig_part);
               }
-              uint16_t h0, l0, h1, l1;
-              if (kSplit) { split16<kBf16>(x0, h0, l0); split16<kBf16>(x1, h1, l1); }
-              else { h0 = cvt16<kBf16>(x0); h1 = cvt16<kBf16>(x1); l0 = l1 = 0; }
-              phi[j >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-              plo[j >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+              split_pair<kBf16, kSplit>(x0, x1, phi[j >> 1], plo[j >> 1]);
             }
             tmem_st16(tbase + lane_base + kColAhi + (c0 >> 1), phi);
             if (kSplit) tmem_st16(tbase + lane_base + kColAlo + (c0 >> 1), plo);
@@ -533,17 +581,27 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
   if (warp == kMmaWarp) tmem_dealloc<512>(tbase);
 }
 
 // ------------------------------------------------------------------ host
-template <bool kBf16, bool kSplit, bool kEmbedded>
+static int tc_cluster_size() {
+  static const int v = [] {
+    const char* e = getenv("SNB_TC_CLUSTER");
+    const int c = e ? atoi(e) : 2;
+    return (c == 1 || c == 2 || c == 4) ? c : 2;
+  }();
+  return v;
+}
+
+template <bool kBf16, bool kSplit, bool kEmbedded, int kCluster>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
   static bool configured = false;
   const size_t smem = sizeof(TcSmem<kSplit>) + 1024;
+  auto kern = field_tc_kernel<kBf16, kSplit, kEmbedded, kCluster>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(field_tc_kernel<kBf16, kSplit, kEmbedded>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(field_tc): %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -552,20 +610,44 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  long long grid = ntiles < sms ? ntiles : sms;
+  grid = (grid + kCluster - 1) / kCluster * kCluster;        // whole clusters
+  if (grid > sms) grid = sms / kCluster * kCluster;
   static const int debug = getenv("SNB_TC_DEBUG") ? atoi(getenv("SNB_TC_DEBUG")) : 0;
   TcParams pd = p;
   pd.debug = debug;
-  field_tc_kernel<kBf16, kSplit, kEmbedded><<<grid, kThreads, smem, st>>>(pd);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, pd);
+  if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "field_tc_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("field_tc_kernel");
+}
+
+template <bool kBf16, bool kSplit, bool kEmbedded>
+static int launch_tc_cluster(const TcParams& p, cudaStream_t st) {
+  switch (tc_cluster_size()) {
+    case 1: return launch_tc<kBf16, kSplit, kEmbedded, 1>(p, st);
+    case 4: return launch_tc<kBf16, kSplit, kEmbedded, 4>(p, st);
+    default: return launch_tc<kBf16, kSplit, kEmbedded, 2>(p, st);
+  }
 }
 
 template <bool kEmbedded>
 static int dispatch_tc(int precision, const TcParams& p, cudaStream_t st) {
   switch (precision) {
-    case SNB_PREC_F16X3: return launch_tc<false, true, kEmbedded>(p, st);
-    case SNB_PREC_BF16X3: return launch_tc<true, true, kEmbedded>(p, st);
-    case SNB_PREC_BF16: return launch_tc<true, false, kEmbedded>(p, st);
+    case SNB_PREC_F16X3: return launch_tc_cluster<false, true, kEmbedded>(p, st);
+    case SNB_PREC_BF16X3: return launch_tc_cluster<true, true, kEmbedded>(p, st);
+    case SNB_PREC_BF16: return launch_tc_cluster<true, false, kEmbedded>(p, st);
   }
   return fail(SNB_ERR_INVALID, "precision %d is not a tensor-core mode", precision);
 }
