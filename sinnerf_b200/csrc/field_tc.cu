@@ -4,14 +4,18 @@
 // [r,g,b,sigma] out; reference models/rendering.py:184-212,284-285 + models/nerf.py:24-41,
 // 105-148), but every 256-wide layer is a chain of tcgen05.mma instructions:
 //
-//   * one persistent CTA per SM, one 128-point tile in flight per CTA;
+//   * persistent CTA PAIRS (cluster of 2, cta_group::2): every MMA is M = 256 -- 128 points of
+//     the even CTA's tile and 128 of the odd CTA's -- and each CTA stages only HALF of every
+//     weight chunk.  Measured reason: an SM ingests ~28 B/clk from L2, and a 1-CTA design needs
+//     2.3 MB of weights per 128-point tile, i.e. 84k cycles of ingest against 56k cycles of MMA;
+//     the pair halves the bytes per SM (probes/umma2_probe.cu validated the 2-CTA forms);
 //   * accumulator D (128 x 256 fp32) in TMEM columns [0,256);
 //   * the NEXT layer's A operand never touches shared memory or HBM: the epilogue warps read
 //     D with tcgen05.ld, add bias, apply ReLU, split the fp32 value into a 16-bit hi part and a
 //     16-bit lo part and write both back to TMEM columns [256,384) / [384,512) with tcgen05.st;
 //     the MMAs read A straight from TMEM (".ts" operand form);
-//   * weights stream from L2 through an 8-stage smem ring of 16 KB chunks (128 output rows x 32 K
-//     x {hi,lo}) with cp.async.bulk (1-D TMA) + mbarrier complete_tx; the packed image is laid
+//   * weights stream from L2 through an 8-stage smem ring of 16 KB chunks (per CTA: 64 output
+//     rows x 64 K x {hi,lo}) with cp.async.bulk (1-D TMA) + mbarrier complete_tx; the packed image is laid
 //     out in exactly the order the MMA warp consumes it, in the SWIZZLE_NONE K-major canonical
 //     core-matrix layout, so one chunk is one contiguous copy;
 //   * fp32 parity (SNB_PREC_F16X3 / BF16X3): x*w ~= xh*wh + xl*wh + xh*wl, three MMAs per K
@@ -39,14 +43,26 @@ namespace snb {
 using namespace umma;
 
 // ------------------------------------------------------------------ geometry
-constexpr int kTile = 128;             // points per tile == MMA M
-constexpr int kNh = 128;               // output rows per chunk == MMA N
-constexpr int kKc = 32;                // K per chunk (2 MMA K-steps)
+constexpr int kTile = 128;             // points per CTA tile (MMA M = 128 * cta_group)
+constexpr int kNh = 128;               // output columns per MMA (N); a 256-wide layer is two halves
 constexpr int kEpiWarps = 8;           // warps 0..7: prologue / epilogue (2 per TMEM lane quadrant)
 constexpr int kMmaWarp = 8, kLoadWarp = 9;
 constexpr int kThreads = 320;
-constexpr int kStages = 8;
+#ifndef SNB_TC_STAGES
+#define SNB_TC_STAGES 10
+#endif
+constexpr int kStages = SNB_TC_STAGES;
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
+
+// per cta_group geometry: a chunk is 128 output rows x kKc of K; each CTA of the group holds
+// kRowsB = 128 / cg of those rows, so a CTA's ring stage is kRowsB * kKc * 2 B (x2 with lo)
+template <int kCg>
+struct Geo {
+  static constexpr int kKc = kCg == 2 ? 64 : 32;
+  static constexpr int kRowsB = kNh / kCg;
+  static constexpr int kSteps = kKc / 16;
+  static constexpr uint32_t kPartBytes = kRowsB * kKc * 2;   // one of {hi, lo} of a CTA's share
+};
 
 enum { SRC_ENC = 0, SRC_HID = 1, SRC_DIR = 2 };
 enum { WAIT_NONE = 0, WAIT_ENC = 1, WAIT_A0 = 2, WAIT_A1 = 3 };
@@ -54,12 +70,12 @@ enum { COMMIT_NONE = 0, COMMIT_D0 = 1, COMMIT_D1 = 2 };
 
 struct Chunk {
   uint8_t layer;   // 0..9 (8 = bottleneck, 9 = direction layer)
-  uint8_t half;    // output rows [128*half, +128)
+  uint8_t half;    // output columns [128*half, +128)
   uint8_t src;     // SRC_*: where the A operand of this chunk lives
-  uint8_t kc;      // chunk index inside that source (K offset = 32*kc)
+  uint8_t kc;      // chunk index inside that source (K offset = kKc*kc)
   uint8_t kpad;    // chunk index in the layer's padded K space (gemm_k)
   uint8_t first;   // first chunk of this (layer, half): accumulate = 0
-  uint8_t wait;    // WAIT_* before issuing
+  uint8_t wait;    // WAIT_* before issuing (low nibble) | K16 steps in this chunk (high nibble)
   uint8_t commit;  // COMMIT_* after issuing
 };
 constexpr int kMaxChunks = 160;
@@ -69,23 +85,28 @@ struct ChunkTable {
   int n_sigma_only;  // chunks per tile through layer 8
 };
 
+template <int KC>
 __host__ __device__ constexpr ChunkTable make_chunk_table() {
   ChunkTable t{};
   int n = 0;
+  constexpr int kHalfChunks = 128 / KC;     // chunks per K half of a hidden layer
+  constexpr int kEncChunks = kXyzPad / KC;  // chunks of the 64-wide xyz embedding
+  constexpr int kStepsFull = KC / 16;
   for (int l = 0; l < kNumGemm; ++l) {
     const bool has_enc = (l == 0 || l == 4);
     const bool has_hid = (l != 0);
-    const int enc_chunks = has_enc ? 2 : 0;
+    const int enc_chunks = has_enc ? kEncChunks : 0;
     if (l == 9) {
       // direction layer: N = 128, one half; A = [bottleneck (TMEM, 256) | dir (smem, 32)]
-      for (int kc = 0; kc < 8; ++kc) {
+      for (int kc = 0; kc < 2 * kHalfChunks; ++kc) {
         Chunk c{};
         c.layer = 9; c.half = 0; c.src = SRC_HID; c.kc = kc; c.kpad = kc; c.first = (kc == 0);
-        c.wait = kc == 0 ? WAIT_A0 : (kc == 4 ? WAIT_A1 : WAIT_NONE);
+        c.wait = (kc == 0 ? WAIT_A0 : (kc == kHalfChunks ? WAIT_A1 : WAIT_NONE)) | (kStepsFull << 4);
         t.c[n++] = c;
       }
       Chunk c{};
-      c.layer = 9; c.src = SRC_DIR; c.kc = 0; c.kpad = 8; c.commit = COMMIT_D0;
+      c.layer = 9; c.src = SRC_DIR; c.kc = 0; c.kpad = 2 * kHalfChunks; c.commit = COMMIT_D0;
+      c.wait = WAIT_NONE | ((kDirPad / 16) << 4);
       t.c[n++] = c;
       continue;
     }
@@ -98,21 +119,25 @@ __host__ __device__ constexpr ChunkTable make_chunk_table() {
         for (int kc = 0; kc < enc_chunks; ++kc) {
           Chunk c{};
           c.layer = l; c.half = half; c.src = SRC_ENC; c.kc = kc; c.kpad = kc; c.first = (kc == 0);
-          if (first_in_phase) c.wait = (l == 0) ? (half == 0 ? WAIT_ENC : WAIT_NONE) : (half == 0 ? WAIT_A0 : WAIT_A1);
+          int w = WAIT_NONE;
+          if (first_in_phase) w = (l == 0) ? (half == 0 ? WAIT_ENC : WAIT_NONE) : (half == 0 ? WAIT_A0 : WAIT_A1);
+          c.wait = w | (kStepsFull << 4);
           first_in_phase = false;
           if (!has_hid && kc == enc_chunks - 1) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
           t.c[n++] = c;
         }
       }
       if (has_hid) {
-        for (int kq = 0; kq < 4; ++kq) {
-          const int kc = khalf * 4 + kq;
+        for (int kq = 0; kq < kHalfChunks; ++kq) {
+          const int kc = khalf * kHalfChunks + kq;
           Chunk c{};
           c.layer = l; c.half = half; c.src = SRC_HID; c.kc = kc; c.kpad = enc_chunks + kc;
           c.first = (!has_enc && kc == 0);
-          if (first_in_phase && khalf == 0) c.wait = half == 0 ? WAIT_A0 : WAIT_A1;
+          int w = WAIT_NONE;
+          if (first_in_phase && khalf == 0) w = half == 0 ? WAIT_A0 : WAIT_A1;
+          c.wait = w | (kStepsFull << 4);
           first_in_phase = false;
-          if (khalf == 1 && kq == 3) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
+          if (khalf == 1 && kq == kHalfChunks - 1) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
           t.c[n++] = c;
         }
       }
@@ -122,9 +147,24 @@ __host__ __device__ constexpr ChunkTable make_chunk_table() {
   t.n_total = n;
   return t;
 }
-__constant__ ChunkTable c_chunks = make_chunk_table();
-static constexpr ChunkTable h_chunks = make_chunk_table();
-static_assert(h_chunks.n_total == 145 && h_chunks.n_sigma_only == 120, "chunk schedule");
+__constant__ ChunkTable c_chunks32 = make_chunk_table<32>();
+__constant__ ChunkTable c_chunks64 = make_chunk_table<64>();
+static constexpr ChunkTable h_chunks32 = make_chunk_table<32>();
+static constexpr ChunkTable h_chunks64 = make_chunk_table<64>();
+static_assert(h_chunks32.n_total == 145 && h_chunks32.n_sigma_only == 120, "chunk schedule (K32)");
+static_assert(h_chunks64.n_total == 73 && h_chunks64.n_sigma_only == 60, "chunk schedule (K64)");
+template <int kCg>
+__device__ __forceinline__ const ChunkTable& chunk_table() { return kCg == 2 ? c_chunks64 : c_chunks32; }
+
+// cta_group used by the tensor-core path (2 unless SNB_TC_CTAGROUP=1); the packed image layout
+// depends on it, so pack and launch read the same value
+static int tc_cta_group() {
+  static const int v = [] {
+    const char* e = getenv("SNB_TC_CTAGROUP");
+    return (e && atoi(e) == 1) ? 1 : 2;
+  }();
+  return v;
+}
 
 // ------------------------------------------------------------------ packed image
 // [PackedHeader 256 B][consts: biases + head weights, fp32][chunk 0][chunk 1]...
@@ -147,11 +187,14 @@ constexpr int kConstFloats = make_const_layout().total;
 constexpr size_t kConstBytes = (size_t)kConstFloats * 4;
 
 __host__ __device__ constexpr bool prec_split(int precision) { return precision != SNB_PREC_BF16; }
-__host__ __device__ constexpr uint32_t chunk_bytes(int precision) {
-  return (uint32_t)(kNh * kKc * 2 * (prec_split(precision) ? 2 : 1));
+// bytes of one chunk in the image (all CTAs' shares): 128 rows x kKc x 2 B (x2 with the lo part)
+__host__ __device__ constexpr uint32_t chunk_bytes(int precision, int kc) {
+  return (uint32_t)(kNh * kc * 2 * (prec_split(precision) ? 2 : 1));
 }
 size_t tc_packed_bytes(int precision) {
-  return sizeof(PackedHeader) + kConstBytes + (size_t)h_chunks.n_total * chunk_bytes(precision);
+  const bool cg2 = tc_cta_group() == 2;
+  return sizeof(PackedHeader) + kConstBytes +
+         (size_t)(cg2 ? h_chunks64.n_total : h_chunks32.n_total) * chunk_bytes(precision, cg2 ? 64 : 32);
 }
 
 // 16-bit conversions -------------------------------------------------------------------
@@ -207,9 +250,11 @@ struct ParamPtrsTc {
   const float* p[SNB_N_PARAM_TENSORS];
 };
 
-template <bool kBf16, bool kSplit>
+template <bool kBf16, bool kSplit, int kCg>
 __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation, unsigned char* image) {
+  using G = Geo<kCg>;
   constexpr ConstLayout CL = make_const_layout();
+  const ChunkTable& tab = chunk_table<kCg>();
   PackedHeader* hdr = reinterpret_cast<PackedHeader*>(image);
   float* cst = reinterpret_cast<float*>(image + sizeof(PackedHeader));
   unsigned char* chunks = image + sizeof(PackedHeader) + kConstBytes;
@@ -218,6 +263,7 @@ __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation
     hdr->magic = kMagic;
     hdr->precision = precision;
     hdr->new_activation = new_activation;
+    hdr->reserved[0] = kCg;
   }
   for (int e = gtid; e < kConstFloats; e += gsz) {
     float v = 0.f;
@@ -231,48 +277,58 @@ __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation
     else if (e >= CL.rgb_b && e < CL.rgb_b + 3) v = pp.p[kRgbB][e - CL.rgb_b];
     cst[e] = v;
   }
-  const uint32_t cbytes = chunk_bytes(precision);
-  const int per_chunk = kNh * kKc;
-  for (int e = gtid; e < c_chunks.n_total * per_chunk; e += gsz) {
+  // chunk image: [CTA 0 share: hi | lo][CTA 1 share: hi | lo]; a share is the canonical
+  // (SWIZZLE_NONE, K-major) block [k8][kRowsB rows][8 elements]
+  constexpr uint32_t kShare = G::kPartBytes * (kSplit ? 2 : 1);
+  constexpr int per_chunk = kNh * G::kKc;
+  for (int e = gtid; e < tab.n_total * per_chunk; e += gsz) {
     const int ci = e / per_chunk, rem = e - ci * per_chunk;
-    const int r = rem / kKc, kk = rem - r * kKc;
-    const Chunk c = c_chunks.c[ci];
+    const int r = rem / G::kKc, kk = rem - r * G::kKc;
+    const Chunk c = tab.c[ci];
     const int l = c.layer;
     const int n = c.half * kNh + r;
-    const int kpad = c.kpad * kKc + kk;
-    const int col = gemm_src_col(l, kpad);
+    const int kpad = c.kpad * G::kKc + kk;
+    const int col = kpad < gemm_k(l) ? gemm_src_col(l, kpad) : -1;
     const int src_k = l == 0 ? 63 : (l == 4 ? 319 : (l == 9 ? 283 : 256));
     const float w = col >= 0 ? pp.p[param_weight_index(l)][n * src_k + col] : 0.f;
-    unsigned char* base = chunks + (size_t)ci * cbytes;
-    const uint32_t off = (uint32_t)(kk >> 3) * (kNh * 16) + r * 16 + (kk & 7) * 2;
+    const int owner = r / G::kRowsB, rr = r - owner * G::kRowsB;
+    unsigned char* base = chunks + (size_t)ci * (kShare * kCg) + (size_t)owner * kShare;
+    const uint32_t off = (uint32_t)(kk >> 3) * (G::kRowsB * 16) + rr * 16 + (kk & 7) * 2;
     if (kSplit) {
       uint16_t hi, lo;
       split16<kBf16>(w, hi, lo);
       *reinterpret_cast<uint16_t*>(base + off) = hi;
-      *reinterpret_cast<uint16_t*>(base + kNh * kKc * 2 + off) = lo;
+      *reinterpret_cast<uint16_t*>(base + G::kPartBytes + off) = lo;
     } else {
       *reinterpret_cast<uint16_t*>(base + off) = cvt16<kBf16>(w);
     }
   }
 }
 
-int launch_pack_tc(const float* const* params, int precision, int new_activation, void* image, cudaStream_t st) {
-  ParamPtrsTc pp;
-  for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i) pp.p[i] = params[i];
-  unsigned char* img = reinterpret_cast<unsigned char*>(image);
-  if (precision == SNB_PREC_F16X3) pack_tc_kernel<false, true><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
-  else if (precision == SNB_PREC_BF16X3) pack_tc_kernel<true, true><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
-  else if (precision == SNB_PREC_BF16) pack_tc_kernel<true, false><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
+template <int kCg>
+static int launch_pack_tc_cg(const ParamPtrsTc& pp, int precision, int new_activation, unsigned char* img,
+                             cudaStream_t st) {
+  if (precision == SNB_PREC_F16X3) pack_tc_kernel<false, true, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
+  else if (precision == SNB_PREC_BF16X3) pack_tc_kernel<true, true, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
+  else if (precision == SNB_PREC_BF16) pack_tc_kernel<true, false, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
   else return fail(SNB_ERR_INVALID, "launch_pack_tc: precision %d is not a tensor-core mode", precision);
   return check_launch("pack_tc_kernel");
 }
 
+int launch_pack_tc(const float* const* params, int precision, int new_activation, void* image, cudaStream_t st) {
+  ParamPtrsTc pp;
+  for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i) pp.p[i] = params[i];
+  unsigned char* img = reinterpret_cast<unsigned char*>(image);
+  return tc_cta_group() == 2 ? launch_pack_tc_cg<2>(pp, precision, new_activation, img, st)
+                             : launch_pack_tc_cg<1>(pp, precision, new_activation, img, st);
+}
+
 // ------------------------------------------------------------------ shared memory
-template <bool kSplit>
+template <bool kSplit, int kCg>
 struct TcSmem {
-  static constexpr uint32_t kChunkBytes = kNh * kKc * 2 * (kSplit ? 2 : 1);
+  static constexpr uint32_t kStageBytes = Geo<kCg>::kPartBytes * (kSplit ? 2 : 1);   // this CTA's share of a chunk
   static constexpr int kParts = kSplit ? 2 : 1;
-  alignas(1024) unsigned char ring[kStages][kChunkBytes];
+  alignas(1024) unsigned char ring[kStages][kStageBytes];
   alignas(128) unsigned char enc[kParts][kTile * kXyzPad * 2];   // canonical [k8][row][8] hi (, lo)
   alignas(128) unsigned char dir[kParts][kTile * kDirPad * 2];
   alignas(16) float cst[kConstFloats];
@@ -292,7 +348,7 @@ struct TcParams {
   long long n_points;
   int sigma_only;
   float* out;
-  int debug;   // timing experiments only (SNB_TC_DEBUG): 1 = loader skips copies, 2 = epilogue skips math, 4 = no MMAs
+  int debug;   // timing experiments only (SNB_TC_DEBUG): 2 = epilogue skips math, 4 = no MMAs
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -300,126 +356,149 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 // canonical (SWIZZLE_NONE, K-major) byte offset of element (row, k) in a [k8][128 rows][8] block
 __device__ __forceinline__ uint32_t canon_off(int row, int k) { return (uint32_t)(k >> 3) * (kTile * 16) + row * 16 + (k & 7) * 2; }
 
-template <bool kBf16, bool kSplit, bool kEmbedded, int kCluster>
+template <bool kBf16, bool kSplit, bool kEmbedded, int kCg>
 __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
-  using Smem = TcSmem<kSplit>;
+  using Smem = TcSmem<kSplit, kCg>;
+  using G = Geo<kCg>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   constexpr ConstLayout CL = make_const_layout();
-  constexpr uint32_t kChunkBytes = Smem::kChunkBytes;
-  constexpr uint32_t kLoOff = kNh * kKc * 2;  // lo block inside a chunk
+  constexpr uint32_t kStageBytes = Smem::kStageBytes;
+  const ChunkTable& tab = chunk_table<kCg>();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(p.image);
   const int new_activation = hdr->new_activation;
   const float* g_cst = reinterpret_cast<const float*>(p.image + sizeof(PackedHeader));
   const unsigned char* g_chunks = p.image + sizeof(PackedHeader) + kConstBytes;
+  const uint32_t cta_rank = kCg == 2 ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  // tile slots: group g (a CTA or a CTA pair) handles tile (g + i * n_groups) * kCg + rank.  Every
+  // CTA of a group runs the same number of slots; slots past the end compute on zeros, store nothing.
   const long long ntiles = (p.n_points + kTile - 1) / kTile;
-  // every CTA runs the same number of tile slots (the weight ring is shared cluster-wide, so the
-  // CTAs of a cluster advance in lock step); slots past the end compute on zeros and store nothing
-  const long long tile_end = ((ntiles + gridDim.x - 1) / gridDim.x) * gridDim.x;
-  constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1);
-  const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
+  const long long n_groups = gridDim.x / kCg, group = blockIdx.x / kCg;
+  const long long n_slots = ((ntiles + kCg - 1) / kCg + n_groups - 1) / n_groups;
   const int n_layers_epi = p.sigma_only ? 8 : 9;   // layers with a TMEM->TMEM epilogue
-  const int n_chunks = p.sigma_only ? c_chunks.n_sigma_only : c_chunks.n_total;
+  const int n_chunks = p.sigma_only ? tab.n_sigma_only : tab.n_total;
 
   // ---------------- one-time setup
   for (int i = tid; i < kConstFloats; i += kThreads) s.cst[i] = g_cst[i];
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], kCluster); }
+    // full: this CTA's loader (+ the peer's relay, at the leader of a pair); a_ready / enc_ready live
+    // at the leader and count the epilogue threads of every CTA of the group
+    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], (kCg == 2 && leader) ? 2 : 1); mbar_init(&s.empty[i], 1); }
     mbar_init(&s.d_full[0], 1); mbar_init(&s.d_full[1], 1);
-    mbar_init(&s.a_ready[0], kEpiWarps * 32); mbar_init(&s.a_ready[1], kEpiWarps * 32);
-    mbar_init(&s.enc_ready, kEpiWarps * 32);
+    mbar_init(&s.a_ready[0], kEpiWarps * 32 * kCg); mbar_init(&s.a_ready[1], kEpiWarps * 32 * kCg);
+    mbar_init(&s.enc_ready, kEpiWarps * 32 * kCg);
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) tmem_alloc<512>(&s.tmem_base);
+  if (warp == kMmaWarp) { if (kCg == 2) tmem_alloc_pair(&s.tmem_base); else tmem_alloc<512>(&s.tmem_base); }
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
+  if (kCg == 2) cluster_sync_all();   // the peer's barriers exist before anyone signals them
   tc_fence_after();
   const uint32_t tbase = s.tmem_base;
 
   if (warp == kLoadWarp) {
     // ======================= weight loader (one elected lane) =======================
+    // streams this CTA's share of every chunk, in schedule order, through the ring
     if (elect_one()) {
       uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      for (long long slot = 0; slot < n_slots; ++slot) {
         for (int ci = 0; ci < n_chunks; ++ci, ++it) {
           const uint32_t st = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(&s.empty[st], ph ^ 1);
-          if ((p.debug & 1) && it >= kStages) { mbar_arrive(&s.full[st]); continue; }
-          mbar_arrive_expect_tx(&s.full[st], kChunkBytes);
-          if (kCluster == 1) {
-            bulk_g2s(s.ring[st], g_chunks + (size_t)ci * kChunkBytes, kChunkBytes, &s.full[st]);
-          } else {
-            // this CTA fetches its 1/kCluster slice of the chunk once from L2 and multicasts it
-            constexpr uint32_t kSlice = kChunkBytes / kCluster;
-            bulk_g2s_multicast(s.ring[st] + cta_rank * kSlice, g_chunks + (size_t)ci * kChunkBytes + cta_rank * kSlice,
-                               kSlice, &s.full[st], kClusterMask);
-          }
+          mbar_arrive_expect_tx(&s.full[st], kStageBytes);
+          bulk_g2s(s.ring[st], g_chunks + ((size_t)ci * kCg + cta_rank) * kStageBytes, kStageBytes, &s.full[st]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp && !leader) {
+    // ======================= relay (odd CTA of a pair) =======================
+    // tells the leader when this CTA's share of a chunk has landed
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (long long slot = 0; slot < n_slots; ++slot) {
+        for (int ci = 0; ci < n_chunks; ++ci, ++it) {
+          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&s.full[st], ph);
+          mbar_arrive_remote(&s.full[st], 0);
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ======================= MMA issuer =======================
+    // ======================= MMA issuer (leader CTA) =======================
     // The whole warp walks the chunk schedule (uniform control flow); one elected lane issues
     // the tcgen05 instructions of a chunk, so they compile to single uniform-datapath ops.
-    const uint32_t idesc = make_idesc(kBf16 ? kFmtBF16 : kFmtF16, kTile, kNh);
+    const uint32_t idesc = make_idesc(kBf16 ? kFmtBF16 : kFmtF16, kTile * kCg, kNh);
     const uint32_t enc_hi = smem_u32(s.enc[0]), dir_hi = smem_u32(s.dir[0]);
     const uint32_t enc_lo = smem_u32(s.enc[kSplit ? 1 : 0]), dir_lo = smem_u32(s.dir[kSplit ? 1 : 0]);
     const uint32_t ring0 = smem_u32(s.ring[0]);
     // descriptor templates: only the 14-bit start-address field changes between MMAs
-    const uint64_t desc_b0 = make_smem_desc(0, kNh * 16, 128);
+    const uint64_t desc_b0 = make_smem_desc(0, G::kRowsB * 16, 128);
     const uint64_t desc_a0 = make_smem_desc(0, kTile * 16, 128);
-    constexpr uint32_t kStepB = (2 * kNh * 16) >> 4;     // one K16 step inside a chunk, in 16-B units
+    constexpr uint32_t kStepB = (2 * G::kRowsB * 16) >> 4;     // one K16 step inside a chunk, in 16-B units
     constexpr uint32_t kStepA = (2 * kTile * 16) >> 4;
+    auto wait_bar = [&](uint64_t* bar, uint32_t ph) { mbar_wait(bar, ph); };
+    auto issue_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) {
+      if (kCg == 2) mma2_ts(d, a, b, idesc, acc); else mma_ts(d, a, b, idesc, acc);
+    };
+    auto issue_ss = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+      if (kCg == 2) mma2_ss(d, a, b, idesc, acc); else mma_ss(d, a, b, idesc, acc);
+    };
+    auto commit = [&](uint64_t* bar) { if (kCg == 2) mma2_commit(bar); else mma_commit(bar); };
     uint32_t it = 0, ph_a0 = 0, ph_a1 = 0, ph_enc = 0;
-    for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+    for (long long slot = 0; slot < n_slots; ++slot) {
       for (int ci = 0; ci < n_chunks; ++ci, ++it) {
-        const Chunk c = c_chunks.c[ci];
-        if (c.wait == WAIT_ENC) { mbar_wait(&s.enc_ready, ph_enc); ph_enc ^= 1; }
-        else if (c.wait == WAIT_A0) { mbar_wait(&s.a_ready[0], ph_a0); ph_a0 ^= 1; }
-        else if (c.wait == WAIT_A1) { mbar_wait(&s.a_ready[1], ph_a1); ph_a1 ^= 1; }
+        const Chunk c = tab.c[ci];
+        const int w = c.wait & 15, steps = c.wait >> 4;
+        if (w == WAIT_ENC) { wait_bar(&s.enc_ready, ph_enc); ph_enc ^= 1; }
+        else if (w == WAIT_A0) { wait_bar(&s.a_ready[0], ph_a0); ph_a0 ^= 1; }
+        else if (w == WAIT_A1) { wait_bar(&s.a_ready[1], ph_a1); ph_a1 ^= 1; }
         const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-        mbar_wait(&s.full[st], ph);
+        wait_bar(&s.full[st], ph);
         tc_fence_after();
-        if (elect_one() && !(p.debug & 4)) {
-          const uint32_t d = tbase + kColD + (c.layer == 9 ? 0 : c.half * kNh);
-          const uint64_t b_hi = desc_b0 + ((ring0 + st * kChunkBytes) >> 4);
-          const uint64_t b_lo = b_hi + (kLoOff >> 4);
-          const uint32_t acc0 = c.first ? 0u : 1u;
-          if (c.src == SRC_HID) {
-            const uint32_t a_hi = tbase + kColAhi + ((uint32_t)(c.kc * kKc) >> 1);
-            const uint32_t a_lo = tbase + kColAlo + ((uint32_t)(c.kc * kKc) >> 1);
-            mma_ts(d, a_hi, b_hi, idesc, acc0);
-            if (kSplit) { mma_ts(d, a_lo, b_hi, idesc, 1); mma_ts(d, a_hi, b_lo, idesc, 1); }
-            mma_ts(d, a_hi + 8, b_hi + kStepB, idesc, 1);
-            if (kSplit) { mma_ts(d, a_lo + 8, b_hi + kStepB, idesc, 1); mma_ts(d, a_hi + 8, b_lo + kStepB, idesc, 1); }
-          } else {
-            const uint32_t a_off = (uint32_t)(c.kc * 4) * (kTile * 16);
-            const uint64_t a_hi = desc_a0 + (((c.src == SRC_ENC ? enc_hi : dir_hi) + a_off) >> 4);
-            const uint64_t a_lo = desc_a0 + (((c.src == SRC_ENC ? enc_lo : dir_lo) + a_off) >> 4);
-            mma_ss(d, a_hi, b_hi, idesc, acc0);
-            if (kSplit) { mma_ss(d, a_lo, b_hi, idesc, 1); mma_ss(d, a_hi, b_lo, idesc, 1); }
-            mma_ss(d, a_hi + kStepA, b_hi + kStepB, idesc, 1);
-            if (kSplit) { mma_ss(d, a_lo + kStepA, b_hi + kStepB, idesc, 1); mma_ss(d, a_hi + kStepA, b_lo + kStepB, idesc, 1); }
+        if (elect_one()) {
+          if (!(p.debug & 4)) {
+            const uint32_t d = tbase + kColD + (c.layer == 9 ? 0 : c.half * kNh);
+            const uint64_t b_hi = desc_b0 + ((ring0 + st * kStageBytes) >> 4);
+            const uint64_t b_lo = b_hi + (G::kPartBytes >> 4);
+            if (c.src == SRC_HID) {
+              const uint32_t a_hi = tbase + kColAhi + ((uint32_t)(c.kc * G::kKc) >> 1);
+              const uint32_t a_lo = tbase + kColAlo + ((uint32_t)(c.kc * G::kKc) >> 1);
+#pragma unroll
+              for (int ks = 0; ks < G::kSteps; ++ks) {
+                issue_ts(d, a_hi + ks * 8, b_hi + ks * kStepB, (c.first && ks == 0) ? 0u : 1u);
+                if (kSplit) {
+                  issue_ts(d, a_lo + ks * 8, b_hi + ks * kStepB, 1);
+                  issue_ts(d, a_hi + ks * 8, b_lo + ks * kStepB, 1);
+                }
+              }
+            } else {
+              const uint32_t a_off = (uint32_t)(c.kc * (G::kKc / 8)) * (kTile * 16);
+              const uint64_t a_hi = desc_a0 + (((c.src == SRC_ENC ? enc_hi : dir_hi) + a_off) >> 4);
+              const uint64_t a_lo = desc_a0 + (((c.src == SRC_ENC ? enc_lo : dir_lo) + a_off) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < G::kSteps; ++ks) {
+                if (ks < steps) {
+                  issue_ss(d, a_hi + ks * kStepA, b_hi + ks * kStepB, (c.first && ks == 0) ? 0u : 1u);
+                  if (kSplit) {
+                    issue_ss(d, a_lo + ks * kStepA, b_hi + ks * kStepB, 1);
+                    issue_ss(d, a_hi + ks * kStepA, b_lo + ks * kStepB, 1);
+                  }
+                }
+              }
+            }
           }
-          // ring slot free (in every CTA of the cluster) once these MMAs retire
-          if (kCluster == 1) mma_commit(&s.empty[st]); else mma_commit_multicast(&s.empty[st], kClusterMask);
-          if (c.commit == COMMIT_D0) mma_commit(&s.d_full[0]);
-          else if (c.commit == COMMIT_D1) mma_commit(&s.d_full[1]);
-        } else if (p.debug & 4) {
-          if (elect_one()) {
-            if (kCluster == 1) mma_commit(&s.empty[st]); else mma_commit_multicast(&s.empty[st], kClusterMask);
-            if (c.commit == COMMIT_D0) mma_commit(&s.d_full[0]);
-            else if (c.commit == COMMIT_D1) mma_commit(&s.d_full[1]);
-          }
+          commit(&s.empty[st]);        // ring slot free (in both CTAs of a pair) once these MMAs retire
+          if (c.commit == COMMIT_D0) commit(&s.d_full[0]);
+          else if (c.commit == COMMIT_D1) commit(&s.d_full[1]);
         }
         __syncwarp();
       }
       if (p.sigma_only) {
         // layer 8's epilogue arrives on a_ready[0..1] with nobody waiting: consume the phases
-        mbar_wait(&s.a_ready[0], ph_a0); ph_a0 ^= 1;
-        mbar_wait(&s.a_ready[1], ph_a1); ph_a1 ^= 1;
+        wait_bar(&s.a_ready[0], ph_a0); ph_a0 ^= 1;
+        wait_bar(&s.a_ready[1], ph_a1); ph_a1 ^= 1;
       }
     }
   } else {
@@ -427,8 +506,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     const int quad = warp & 3, ch = warp >> 2;       // TMEM lane quadrant, column half
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    // hand-off to the MMA issuer, which lives in the leader CTA
+    auto signal = [&](uint64_t* bar) { if (kCg == 2 && !leader) mbar_arrive_remote(bar, 0); else mbar_arrive(bar); };
     uint32_t ph_d[2] = {0, 0};
-    for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+    for (long long slot = 0; slot < n_slots; ++slot) {
+      const long long tile = (group + slot * n_groups) * kCg + cta_rank;
       const long long p0 = tile * kTile;
       const long long pt = p0 + row;
       // ---------------- prologue: positional encodings -> smem (canonical, hi/lo)
@@ -490,7 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           }
         }
         fence_proxy_async_smem();     // generic-proxy smem writes -> visible to tcgen05.mma
-        mbar_arrive(&s.enc_ready);
+        signal(&s.enc_ready);
       }
 
       float sig_part = 0.f;
@@ -526,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           }
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&s.a_ready[h]);
+          signal(&s.a_ready[h]);
         }
         if (l == 7) {
           // sigma head (nerf.py:136): combine the two column halves of each row
@@ -581,25 +663,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
-  if (warp == kMmaWarp) tmem_dealloc<512>(tbase);
+  if (kCg == 2) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while its peer may still touch it
+  if (warp == kMmaWarp) { if (kCg == 2) tmem_dealloc_pair(tbase); else tmem_dealloc<512>(tbase); }
 }
 
 // ------------------------------------------------------------------ host
-static int tc_cluster_size() {
-  static const int v = [] {
-    const char* e = getenv("SNB_TC_CLUSTER");
-    const int c = e ? atoi(e) : 2;
-    return (c == 1 || c == 2 || c == 4) ? c : 2;
-  }();
-  return v;
-}
-
-template <bool kBf16, bool kSplit, bool kEmbedded, int kCluster>
+template <bool kBf16, bool kSplit, bool kEmbedded, int kCg>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
   static bool configured = false;
-  const size_t smem = sizeof(TcSmem<kSplit>) + 1024;
-  auto kern = field_tc_kernel<kBf16, kSplit, kEmbedded, kCluster>;
+  const size_t smem = sizeof(TcSmem<kSplit, kCg>) + 1024;
+  auto kern = field_tc_kernel<kBf16, kSplit, kEmbedded, kCg>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(field_tc): %s", cudaGetErrorString(e));
@@ -610,20 +683,19 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long grid = ntiles < sms ? ntiles : sms;
-  grid = (grid + kCluster - 1) / kCluster * kCluster;        // whole clusters
-  if (grid > sms) grid = sms / kCluster * kCluster;
+  long long groups = (ntiles + kCg - 1) / kCg;
+  if (groups > sms / kCg) groups = sms / kCg;
   static const int debug = getenv("SNB_TC_DEBUG") ? atoi(getenv("SNB_TC_DEBUG")) : 0;
   TcParams pd = p;
   pd.debug = debug;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
+  cfg.gridDim = dim3((unsigned)(groups * kCg));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.x = kCg;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -634,20 +706,16 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
 }
 
 template <bool kBf16, bool kSplit, bool kEmbedded>
-static int launch_tc_cluster(const TcParams& p, cudaStream_t st) {
-  switch (tc_cluster_size()) {
-    case 1: return launch_tc<kBf16, kSplit, kEmbedded, 1>(p, st);
-    case 4: return launch_tc<kBf16, kSplit, kEmbedded, 4>(p, st);
-    default: return launch_tc<kBf16, kSplit, kEmbedded, 2>(p, st);
-  }
+static int launch_tc_cg(const TcParams& p, cudaStream_t st) {
+  return tc_cta_group() == 2 ? launch_tc<kBf16, kSplit, kEmbedded, 2>(p, st) : launch_tc<kBf16, kSplit, kEmbedded, 1>(p, st);
 }
 
 template <bool kEmbedded>
 static int dispatch_tc(int precision, const TcParams& p, cudaStream_t st) {
   switch (precision) {
-    case SNB_PREC_F16X3: return launch_tc_cluster<false, true, kEmbedded>(p, st);
-    case SNB_PREC_BF16X3: return launch_tc_cluster<true, true, kEmbedded>(p, st);
-    case SNB_PREC_BF16: return launch_tc_cluster<true, false, kEmbedded>(p, st);
+    case SNB_PREC_F16X3: return launch_tc_cg<false, true, kEmbedded>(p, st);
+    case SNB_PREC_BF16X3: return launch_tc_cg<true, true, kEmbedded>(p, st);
+    case SNB_PREC_BF16: return launch_tc_cg<true, false, kEmbedded>(p, st);
   }
   return fail(SNB_ERR_INVALID, "precision %d is not a tensor-core mode", precision);
 }
