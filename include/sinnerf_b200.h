@@ -120,6 +120,30 @@ int snb_importance_merge(const float* z_coarse, const float* weights_coarse, con
                          int64_t u_stride, int64_t n_rays, int n_samples, int n_importance, float eps,
                          float* z_fine, float* z_new, void* stream);
 
+/* ---- training: forward that keeps activations, and the backward ------------------------ */
+
+/* The fused field pass of snb_field_forward in SNB_PREC_FP32 arithmetic, additionally keeping what the
+ * backward needs (the reference keeps the same tensors inside autograd): the two embeddings and every
+ * layer's post-activation output, as plain row-major fp32 tensors.  P = n_rays * n_samples.
+ *   save_enc (P,64)  save_dir (P,32)  save_h (9,P,256) [h1..h8, bottleneck]  save_g (P,128) */
+int snb_field_forward_train(const void* packed_fp32, const float* rays, const float* z_vals, int64_t n_rays,
+                            int n_samples, float* raw, float* save_enc, float* save_dir, float* save_h,
+                            float* save_g, void* stream);
+
+/* Backward of models/rendering.py:215-248 (closed form).  g_rgb (N,3), g_depth (N,),
+ * g_weights (N,S) are dL/d(outputs), any may be NULL (= 0).  -> g_raw (N,S,4) = dL/d[rgb, sigma]. */
+int snb_composite_backward(const float* raw, const float* z_vals, const float* rays, const float* noise,
+                           float noise_std, int white_back, const float* g_rgb, const float* g_depth,
+                           const float* g_weights, int64_t n_rays, int n_samples, float* g_raw, void* stream);
+
+/* Backward of NeRF.forward (autograd through models/nerf.py:105-148) for one field pass.
+ * params / grads: HOST arrays of 24 device pointers in state-dict order; grads are ACCUMULATED into
+ * (zero them first).  ws_a, ws_b (P,256) and ws_s (P,128) are scratch.  No gradient reaches rays or z. */
+int snb_field_backward(const float* const* params, float* const* grads, int new_activation,
+                       const float* g_raw, const float* raw, const float* save_enc, const float* save_dir,
+                       const float* save_h, const float* save_g, int64_t n_points, float* ws_a, float* ws_b,
+                       float* ws_s, void* stream);
+
 /* ---- whole path -------------------------------------------------------------------- */
 typedef struct SnbRenderArgs {
   const float* rays;        /* (N,8)                                                    */

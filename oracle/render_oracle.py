@@ -255,7 +255,8 @@ def render_rays(coarse: Params, fine: Optional[Params], rays: Tensor, N_samples:
         if not det and "pdf_u" not in rng:
             rng["pdf_u"] = torch.rand(n, N_importance)         # RNG call 3 (:43)
         z_new = sample_pdf(z_mid, c["weights"][:, 1:-1], N_importance, det=det,
-                           u=None if det else rng["pdf_u"].to(rays.dtype))
+                           u=None if det else rng["pdf_u"].to(rays.dtype)).detach()
+        # ^ detach: no gradient flows from the fine pass into the coarse weights (:311-313)
         z_f, _ = torch.sort(torch.cat([z, z_new], dim=-1), dim=-1)   # :315
         if z_fine_override is not None:
             z_f = z_fine_override

@@ -38,6 +38,12 @@ int launch_importance_merge(const float*, const float*, const float*, int64_t, i
 int launch_pack_fp32(const float* const*, int, void*, cudaStream_t);
 int field_forward_fp32(const void*, const float*, const float*, int64_t, int, int, float*, cudaStream_t);
 int mlp_forward_fp32(const void*, const float*, int64_t, int64_t, int, float*, cudaStream_t);
+int field_forward_train_fp32(const void*, const float*, const float*, int64_t, int, float*, float*, float*, float*,
+                             float*, cudaStream_t);
+int launch_composite_bwd(const float*, const float*, const float*, const float*, float, int, const float*,
+                         const float*, const float*, int64_t, int, float*, cudaStream_t);
+int field_backward_fp32(const float* const*, float* const*, int, const float*, const float*, const float*,
+                        const float*, const float*, const float*, int64_t, float*, float*, float*, cudaStream_t);
 // tensor-core modes (field_tc.cu)
 size_t tc_packed_bytes(int precision);
 int launch_pack_tc(const float* const*, int, int, void*, cudaStream_t);
@@ -143,7 +149,7 @@ int snb_composite_forward(const float* raw, int raw_channels, const float* z_val
   SNB_REQUIRE(raw_channels == 4 || raw_channels == 1, "snb_composite_forward: raw_channels must be 4 or 1");
   SNB_REQUIRE(n_rays >= 0 && n_samples >= 1, "snb_composite_forward: bad extents");
   SNB_REQUIRE(n_rays == 0 || (raw && z_vals && rays && weights), "snb_composite_forward: null pointer");
-  SNB_REQUIRE(raw_channels == 1 || (rgb && depth), "snb_composite_forward: rgb/depth outputs required");
+  SNB_REQUIRE(n_rays == 0 || raw_channels == 1 || (rgb && depth), "snb_composite_forward: rgb/depth outputs required");
   SNB_REQUIRE(raw_channels == 1 || aligned16(raw), "snb_composite_forward: raw must be 16-byte aligned");
   const float* nz = (noise_std != 0.f) ? noise : nullptr;
   return launch_composite(raw, raw_channels, z_vals, rays, nz, noise_std, white_back, n_rays, n_samples, rgb,
@@ -170,6 +176,43 @@ int snb_importance_merge(const float* z_coarse, const float* weights_coarse, con
   SNB_REQUIRE(u_stride == 0 || u_stride >= n_importance, "snb_importance_merge: bad u stride");
   return launch_importance_merge(z_coarse, weights_coarse, u, u_stride, n_rays, n_samples, n_importance, eps,
                                  z_fine, z_new, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int snb_field_forward_train(const void* packed_fp32, const float* rays, const float* z_vals, int64_t n_rays,
+                            int n_samples, float* raw, float* save_enc, float* save_dir, float* save_h,
+                            float* save_g, void* stream) {
+  SNB_REQUIRE(n_rays >= 0 && n_samples >= 1, "snb_field_forward_train: bad extents");
+  SNB_REQUIRE(n_rays == 0 || (packed_fp32 && rays && z_vals && raw && save_enc && save_dir && save_h && save_g),
+              "snb_field_forward_train: null pointer");
+  SNB_REQUIRE(aligned16(rays) && aligned16(raw) && aligned16(save_h) && aligned16(save_g),
+              "snb_field_forward_train: buffers must be 16-byte aligned");
+  return field_forward_train_fp32(packed_fp32, rays, z_vals, n_rays, n_samples, raw, save_enc, save_dir, save_h,
+                                  save_g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int snb_composite_backward(const float* raw, const float* z_vals, const float* rays, const float* noise,
+                           float noise_std, int white_back, const float* g_rgb, const float* g_depth,
+                           const float* g_weights, int64_t n_rays, int n_samples, float* g_raw, void* stream) {
+  SNB_REQUIRE(n_rays >= 0 && n_samples >= 1, "snb_composite_backward: bad extents");
+  SNB_REQUIRE(n_rays == 0 || (raw && z_vals && rays && g_raw), "snb_composite_backward: null pointer");
+  SNB_REQUIRE(aligned16(raw) && aligned16(g_raw), "snb_composite_backward: raw / g_raw must be 16-byte aligned");
+  const float* nz = (noise_std != 0.f) ? noise : nullptr;
+  return launch_composite_bwd(raw, z_vals, rays, nz, noise_std, white_back, g_rgb, g_depth, g_weights, n_rays,
+                              n_samples, g_raw, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int snb_field_backward(const float* const* params, float* const* grads, int new_activation, const float* g_raw,
+                       const float* raw, const float* save_enc, const float* save_dir, const float* save_h,
+                       const float* save_g, int64_t n_points, float* ws_a, float* ws_b, float* ws_s,
+                       void* stream) {
+  SNB_REQUIRE(n_points >= 0, "snb_field_backward: negative point count");
+  SNB_REQUIRE(params && grads, "snb_field_backward: null parameter arrays");
+  for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i)
+    SNB_REQUIRE(params[i] && grads[i], "snb_field_backward: parameter / gradient tensor %d is null", i);
+  SNB_REQUIRE(n_points == 0 || (g_raw && raw && save_enc && save_dir && save_h && save_g && ws_a && ws_b && ws_s),
+              "snb_field_backward: null pointer");
+  return field_backward_fp32(params, grads, new_activation, g_raw, raw, save_enc, save_dir, save_h, save_g,
+                             n_points, ws_a, ws_b, ws_s, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int snb_render_forward(const SnbRenderArgs* a, void* stream) {

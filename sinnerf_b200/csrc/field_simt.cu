@@ -61,7 +61,9 @@ enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SOFTPLUS = 2 };
 template <int N>
 __device__ __forceinline__ void gemm_layer(FieldSmem& s, const float* __restrict__ Wt,
                                            const float* __restrict__ bias, const float* A0, int K0,
-                                           const float* A1, int K1, int act, float* out) {
+                                           const float* A1, int K1, int act, float* out,
+                                           float* __restrict__ save = nullptr, long long p0 = 0,
+                                           long long n_points = 0) {
   constexpr int NJ = N / 64;  // float4 column chunks per thread
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
@@ -115,17 +117,29 @@ __device__ __forceinline__ void gemm_layer(FieldSmem& s, const float* __restrict
     for (int jj = 0; jj < 4; ++jj) {
       const int c = j * 64 + tx * 4 + jj;
       const float b = __ldg(bias + c);
-      float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float x = acc[i][j * 4 + jj] + b;
         if (act == ACT_RELU) x = fmaxf(x, 0.f);
         else if (act == ACT_SOFTPLUS) x = shifted_softplus_f(x);
-        v[i] = x;
+        acc[i][j * 4 + jj] = x;
       }
       float* op = out + c * TM + ((ty ^ ((c >> 2) & 15)) << 3);
-      *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      *reinterpret_cast<float4*>(op) = make_float4(acc[0][j * 4 + jj], acc[1][j * 4 + jj], acc[2][j * 4 + jj], acc[3][j * 4 + jj]);
+      *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4][j * 4 + jj], acc[5][j * 4 + jj], acc[6][j * 4 + jj], acc[7][j * 4 + jj]);
+    }
+  }
+  // training forward: keep the layer output, (P, N) row-major, for the backward kernels
+  if (save != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long row = p0 + ty * 8 + i;
+      if (row < n_points) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          *reinterpret_cast<float4*>(save + row * N + j * 64 + tx * 4) =
+              make_float4(acc[i][j * 4], acc[i][j * 4 + 1], acc[i][j * 4 + 2], acc[i][j * 4 + 3]);
+      }
     }
   }
   __syncthreads();
@@ -143,6 +157,11 @@ struct FieldParams {
   long long n_points;
   int sigma_only;
   float* out;            // (P,4) or (P,)
+  // training forward (all nullable together): activations kept for field_bwd.cu
+  float* save_enc;       // (P,64)  xyz embedding, pad column zero
+  float* save_dir;       // (P,32)  dir embedding, pad columns zero
+  float* save_h;         // (9,P,256) h1..h8 (post-ReLU) and the bottleneck
+  float* save_g;         // (P,128) direction layer output (post-activation)
 };
 
 template <bool kEmbedded>
@@ -213,15 +232,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_simt_kernel(FieldParams p) 
       }
     }
     __syncthreads();
+    const bool saving = p.save_h != nullptr;
+    if (saving) {
+      for (int e = tid; e < TM * 96; e += NTHREADS) {
+        const int r = e / 96, k = e - r * 96;
+        if (p0 + r < p.n_points) {
+          if (k < kXyzPad) p.save_enc[(p0 + r) * kXyzPad + k] = s.enc[aidx(k, r)];
+          else p.save_dir[(p0 + r) * kDirPad + (k - kXyzPad)] = s.dir[aidx(k - kXyzPad, r)];
+        }
+      }
+    }
+    auto save_ptr = [&](int l) { return saving ? p.save_h + (size_t)l * p.n_points * kWidth : nullptr; };
 
     // ---------------- trunk: 8 layers, skip at layer 5 (index 4) ----------------
-    gemm_layer<256>(s, W + L.w[0], W + L.b[0], s.enc, 64, nullptr, 0, ACT_RELU, s.act);
+    gemm_layer<256>(s, W + L.w[0], W + L.b[0], s.enc, 64, nullptr, 0, ACT_RELU, s.act, save_ptr(0), p0, p.n_points);
 #pragma unroll 1
     for (int l = 1; l < 8; ++l) {
       if (l == 4)
-        gemm_layer<256>(s, W + L.w[4], W + L.b[4], s.enc, 64, s.act, 256, ACT_RELU, s.act);
+        gemm_layer<256>(s, W + L.w[4], W + L.b[4], s.enc, 64, s.act, 256, ACT_RELU, s.act, save_ptr(4), p0, p.n_points);
       else
-        gemm_layer<256>(s, W + L.w[l], W + L.b[l], s.act, 256, nullptr, 0, ACT_RELU, s.act);
+        gemm_layer<256>(s, W + L.w[l], W + L.b[l], s.act, 256, nullptr, 0, ACT_RELU, s.act, save_ptr(l), p0, p.n_points);
     }
     // ---------------- sigma head (no activation, nerf.py:136) ----------------
     {
@@ -242,9 +272,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_simt_kernel(FieldParams p) 
     if (p.sigma_only) continue;  // uniform across the CTA
 
     // ---------------- bottleneck (no activation) + direction layer ----------------
-    gemm_layer<256>(s, W + L.w[8], W + L.b[8], s.act, 256, nullptr, 0, ACT_NONE, s.act);
+    gemm_layer<256>(s, W + L.w[8], W + L.b[8], s.act, 256, nullptr, 0, ACT_NONE, s.act, save_ptr(8), p0, p.n_points);
     gemm_layer<128>(s, W + L.w[9], W + L.b[9], s.act, 256, s.dir, 32,
-                    new_activation ? ACT_SOFTPLUS : ACT_RELU, s.act);
+                    new_activation ? ACT_SOFTPLUS : ACT_RELU, s.act, saving ? p.save_g : nullptr, p0, p.n_points);
     // ---------------- rgb head ----------------
     {
       const int r = tid & (TM - 1), h = tid >> 7;
@@ -301,6 +331,21 @@ static int launch_field_simt(const FieldParams& p, cudaStream_t st) {
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   field_simt_kernel<kEmbedded><<<grid, NTHREADS, smem, st>>>(p);
   return check_launch("field_simt_kernel");
+}
+
+int field_forward_train_fp32(const void* packed, const float* rays, const float* z, int64_t n_rays, int n_samples,
+                             float* raw, float* save_enc, float* save_dir, float* save_h, float* save_g,
+                             cudaStream_t st) {
+  FieldParams p{};
+  p.hdr = reinterpret_cast<const PackedHeader*>(packed);
+  p.rays = rays;
+  p.z = z;
+  p.n_samples = n_samples;
+  p.n_points = (long long)n_rays * n_samples;
+  p.sigma_only = 0;
+  p.out = raw;
+  p.save_enc = save_enc; p.save_dir = save_dir; p.save_h = save_h; p.save_g = save_g;
+  return launch_field_simt<false>(p, st);
 }
 
 int field_forward_fp32(const void* packed, const float* rays, const float* z, int64_t n_rays,

@@ -27,14 +27,19 @@
 //   * sigma (256->1) and rgb (128->3) heads are fp32 dot products inside the epilogue.
 //
 // Schedule inside a layer (N = 256 split in halves a|b, K = 256 in halves 0|1):
-//     (a,k0) (b,k0) (a,k1) -> D_a full -> (b,k1) -> D_b full
-// The epilogue of half a overlaps MMA (b,k1); the epilogue of half b overlaps the next layer's
-// (a,k0): an epilogue half has a quarter of a layer's MMA time to stay hidden.
+//     (a,k0) (a,k1) -> D_a full | (b,k0) -> A[k0] free | (b,k1) -> D_b full
+// Epilogue a (reads D_a, writes the next layer's A[k0]) overlaps both b phases -- it only has to
+// hold its stores until (b,k0), the last reader of A[k0], has retired; epilogue b overlaps the
+// next layer's (a,k0).  Measured with the clock64 trace (tools/trace_field.py): an epilogue half
+// costs ~1800 cycles against 1536 per MMA phase, so the older interleaved order stalled ~1000
+// cycles per layer.
 //
 // Roofline: tensor pipe.  Executed MMA FLOPs are 3x the algorithmic 1 186 816 FLOP/point in the
 // split modes.  HBM traffic: 4 B/point in (z) + 16 B/point out; weights (2.3 MB per tile pass)
 // are L2 hits.
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -65,8 +70,10 @@ struct Geo {
 };
 
 enum { SRC_ENC = 0, SRC_HID = 1, SRC_DIR = 2 };
-enum { WAIT_NONE = 0, WAIT_ENC = 1, WAIT_A0 = 2, WAIT_A1 = 3 };
-enum { COMMIT_NONE = 0, COMMIT_D0 = 1, COMMIT_D1 = 2 };
+// WAIT_A0..A3: the previous layer's epilogue has stored output columns [64q, 64q+64) (= this layer's K
+// quarter q) into the A operand; A0 / A2 also mean accumulator half a / b has been drained.
+enum { WAIT_NONE = 0, WAIT_ENC = 1, WAIT_DIR = 2, WAIT_A0 = 4, WAIT_A1 = 5, WAIT_A2 = 6, WAIT_A3 = 7 };
+enum { COMMIT_NONE = 0, COMMIT_D0 = 1, COMMIT_D1 = 2, COMMIT_AFREE = 4 };   // bit flags
 
 struct Chunk {
   uint8_t layer;   // 0..9 (8 = bottleneck, 9 = direction layer)
@@ -101,43 +108,43 @@ __host__ __device__ constexpr ChunkTable make_chunk_table() {
       for (int kc = 0; kc < 2 * kHalfChunks; ++kc) {
         Chunk c{};
         c.layer = 9; c.half = 0; c.src = SRC_HID; c.kc = kc; c.kpad = kc; c.first = (kc == 0);
-        c.wait = (kc == 0 ? WAIT_A0 : (kc == kHalfChunks ? WAIT_A1 : WAIT_NONE)) | (kStepsFull << 4);
+        const int kq = kc * KC;   // K offset; a new quarter starts every 64
+        c.wait = ((kq % 64 == 0) ? (WAIT_A0 + kq / 64) : WAIT_NONE) | (kStepsFull << 4);
         t.c[n++] = c;
       }
       Chunk c{};
       c.layer = 9; c.src = SRC_DIR; c.kc = 0; c.kpad = 2 * kHalfChunks; c.commit = COMMIT_D0;
-      c.wait = WAIT_NONE | ((kDirPad / 16) << 4);
+      c.wait = WAIT_DIR | ((kDirPad / 16) << 4);
       t.c[n++] = c;
       continue;
     }
-    // phases: (a: enc, hid k0) (b: enc, hid k0) (a: hid k1 -> D_a) (b: hid k1 -> D_b)
-    for (int phase = 0; phase < 4; ++phase) {
-      const int half = phase & 1;
-      const int khalf = phase >> 1;
-      bool first_in_phase = true;
-      if (khalf == 0) {
-        for (int kc = 0; kc < enc_chunks; ++kc) {
-          Chunk c{};
-          c.layer = l; c.half = half; c.src = SRC_ENC; c.kc = kc; c.kpad = kc; c.first = (kc == 0);
-          int w = WAIT_NONE;
-          if (first_in_phase) w = (l == 0) ? (half == 0 ? WAIT_ENC : WAIT_NONE) : (half == 0 ? WAIT_A0 : WAIT_A1);
-          c.wait = w | (kStepsFull << 4);
-          first_in_phase = false;
-          if (!has_hid && kc == enc_chunks - 1) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
-          t.c[n++] = c;
-        }
+    // order: half a (enc, hid k0, hid k1) -> D_a | half b (enc, hid k0) -> A[k0] free | (hid k1) -> D_b
+    for (int half = 0; half < 2; ++half) {
+      bool first = true;
+      for (int kc = 0; kc < enc_chunks; ++kc) {
+        Chunk c{};
+        c.layer = l; c.half = half; c.src = SRC_ENC; c.kc = kc; c.kpad = kc; c.first = first;
+        int w = WAIT_NONE;
+        // layer 1 reads only the embedding; the skip layer's half a overwrites D_a (drained => A0)
+        if (first && half == 0) w = (l == 0) ? WAIT_ENC : WAIT_A0;
+        c.wait = w | (kStepsFull << 4);
+        first = false;
+        if (!has_hid && kc == enc_chunks - 1) c.commit = half == 0 ? COMMIT_D0 : (COMMIT_D1 | COMMIT_AFREE);
+        t.c[n++] = c;
       }
       if (has_hid) {
-        for (int kq = 0; kq < kHalfChunks; ++kq) {
-          const int kc = khalf * kHalfChunks + kq;
+        for (int kc = 0; kc < 2 * kHalfChunks; ++kc) {
           Chunk c{};
-          c.layer = l; c.half = half; c.src = SRC_HID; c.kc = kc; c.kpad = enc_chunks + kc;
-          c.first = (!has_enc && kc == 0);
+          c.layer = l; c.half = half; c.src = SRC_HID; c.kc = kc; c.kpad = enc_chunks + kc; c.first = first;
+          first = false;
+          const int koff = kc * KC;
           int w = WAIT_NONE;
-          if (first_in_phase && khalf == 0) w = half == 0 ? WAIT_A0 : WAIT_A1;
+          // half a consumes the K quarters as the previous layer's epilogue delivers them; by the
+          // time half b starts, all four are known and D_b is drained (A2/A3 imply it)
+          if (half == 0 && koff % 64 == 0) w = (has_enc && koff == 0) ? WAIT_NONE : WAIT_A0 + koff / 64;
           c.wait = w | (kStepsFull << 4);
-          first_in_phase = false;
-          if (khalf == 1 && kq == kHalfChunks - 1) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
+          if (kc == 2 * kHalfChunks - 1) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
+          if (half == 1 && kc == kHalfChunks - 1) c.commit = COMMIT_AFREE;
           t.c[n++] = c;
         }
       }
@@ -218,7 +225,7 @@ __device__ __forceinline__ void split16(float x, uint16_t& hi, uint16_t& lo) {
 
 // Two values at once, with the packed converts (F2FP.*.PACK_AB, full-rate pipe) instead of four
 // scalar F2F (quarter-rate MIO pipe): hi = pack(x0, x1); lo = pack(x0 - up(hi.x), x1 - up(hi.y)).
-template <bool kBf16, bool kSplit>
+template <bool kBf16, bool kSplit, bool kNonNeg = false>
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   if (kBf16) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
@@ -231,8 +238,8 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
       lo = 0;
     }
   } else {
-    x0 = fminf(fmaxf(x0, -65504.f), 65504.f);
-    x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+    if (kNonNeg) { x0 = fminf(x0, 65504.f); x1 = fminf(x1, 65504.f); }   // ReLU output: one-sided
+    else { x0 = fminf(fmaxf(x0, -65504.f), 65504.f); x1 = fminf(fmaxf(x1, -65504.f), 65504.f); }
     const __half2 h = __floats2half2_rn(x0, x1);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     if (kSplit) {
@@ -243,6 +250,15 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
       lo = 0;
     }
   }
+}
+
+// softplus(x - 1) with the hardware ex2 / lg2 approximations (abs error ~1e-7 on an O(1..200)
+// value; the accurate expf/log1pf pair cost the dir-layer epilogue ~10k cycles per tile).
+__device__ __forceinline__ float shifted_softplus_fast(float x) {
+  const float s = x - 1.0f;
+  const float t = __expf(-fabsf(s));                                   // (0, 1]
+  const float lp = t < 9.765625e-4f ? t * (1.0f - 0.5f * t) : __logf(1.0f + t);   // log1p(t)
+  return fmaxf(s, 0.0f) + lp;
 }
 
 // ------------------------------------------------------------------ pack kernel
@@ -334,7 +350,7 @@ struct TcSmem {
   alignas(16) float cst[kConstFloats];
   float part[2][4][kTile];        // head partial sums [column half][sigma,r,g,b][row]
   uint64_t full[kStages], empty[kStages];
-  uint64_t d_full[2], a_ready[2], enc_ready;
+  uint64_t d_full[2], a_ready[4], a_free, enc_ready, dir_ready, d_drained;
   uint32_t tmem_base;
 };
 
@@ -350,6 +366,11 @@ struct TcParams {
   float* out;
   int debug;   // timing experiments only (SNB_TC_DEBUG): 2 = epilogue skips math, 4 = no MMAs
 };
+
+// ---- debug trace (SNB_TC_DEBUG & 8): clock64 stamps of one slot of cluster 0's leader CTA
+constexpr int kTraceLen = 2048;
+__device__ long long g_trace[kTraceLen];
+__device__ __forceinline__ void trace(bool on, int idx) { if (on && idx < kTraceLen) g_trace[idx] = clock64(); }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -386,9 +407,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     // full: this CTA's loader (+ the peer's relay, at the leader of a pair); a_ready / enc_ready live
     // at the leader and count the epilogue threads of every CTA of the group
     for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], (kCg == 2 && leader) ? 2 : 1); mbar_init(&s.empty[i], 1); }
-    mbar_init(&s.d_full[0], 1); mbar_init(&s.d_full[1], 1);
-    mbar_init(&s.a_ready[0], kEpiWarps * 32 * kCg); mbar_init(&s.a_ready[1], kEpiWarps * 32 * kCg);
+    mbar_init(&s.d_full[0], 1); mbar_init(&s.d_full[1], 1); mbar_init(&s.a_free, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&s.a_ready[i], kEpiWarps * 32 * kCg);
     mbar_init(&s.enc_ready, kEpiWarps * 32 * kCg);
+    mbar_init(&s.dir_ready, kEpiWarps * 32 * kCg);
+    mbar_init(&s.d_drained, kEpiWarps * 32 * kCg);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { if (kCg == 2) tmem_alloc_pair(&s.tmem_base); else tmem_alloc<512>(&s.tmem_base); }
@@ -446,17 +469,23 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       if (kCg == 2) mma2_ss(d, a, b, idesc, acc); else mma_ss(d, a, b, idesc, acc);
     };
     auto commit = [&](uint64_t* bar) { if (kCg == 2) mma2_commit(bar); else mma_commit(bar); };
-    uint32_t it = 0, ph_a0 = 0, ph_a1 = 0, ph_enc = 0;
+    uint32_t it = 0, ph_a = 0, ph_enc = 0, ph_dir = 0, ph_drain = 0;   // ph_a: bit q = parity of a_ready[q]
     for (long long slot = 0; slot < n_slots; ++slot) {
+      Chunk c_next = tab.c[0];
       for (int ci = 0; ci < n_chunks; ++ci, ++it) {
-        const Chunk c = tab.c[ci];
+        const Chunk c = c_next;
+        c_next = tab.c[ci + 1 < n_chunks ? ci + 1 : 0];   // prefetch the next entry (constant-cache latency)
         const int w = c.wait & 15, steps = c.wait >> 4;
+        const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3 && lane == 0;
+        trace(tr, ci * 4 + 0);
         if (w == WAIT_ENC) { wait_bar(&s.enc_ready, ph_enc); ph_enc ^= 1; }
-        else if (w == WAIT_A0) { wait_bar(&s.a_ready[0], ph_a0); ph_a0 ^= 1; }
-        else if (w == WAIT_A1) { wait_bar(&s.a_ready[1], ph_a1); ph_a1 ^= 1; }
+        else if (w == WAIT_DIR) { wait_bar(&s.dir_ready, ph_dir); ph_dir ^= 1; }
+        else if (w >= WAIT_A0) { const int q = w - WAIT_A0; wait_bar(&s.a_ready[q], (ph_a >> q) & 1); ph_a ^= 1u << q; }
         const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+        trace(tr, ci * 4 + 1);
         wait_bar(&s.full[st], ph);
         tc_fence_after();
+        trace(tr, ci * 4 + 2);
         if (elect_one()) {
           if (!(p.debug & 4)) {
             const uint32_t d = tbase + kColD + (c.layer == 9 ? 0 : c.half * kNh);
@@ -490,15 +519,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
             }
           }
           commit(&s.empty[st]);        // ring slot free (in both CTAs of a pair) once these MMAs retire
-          if (c.commit == COMMIT_D0) commit(&s.d_full[0]);
-          else if (c.commit == COMMIT_D1) commit(&s.d_full[1]);
+          if (c.commit & COMMIT_AFREE) commit(&s.a_free);
+          if (c.commit & COMMIT_D0) commit(&s.d_full[0]);
+          if (c.commit & COMMIT_D1) commit(&s.d_full[1]);
         }
         __syncwarp();
+        trace(tr, ci * 4 + 3);
       }
       if (p.sigma_only) {
-        // layer 8's epilogue arrives on a_ready[0..1] with nobody waiting: consume the phases
-        wait_bar(&s.a_ready[0], ph_a0); ph_a0 ^= 1;
-        wait_bar(&s.a_ready[1], ph_a1); ph_a1 ^= 1;
+        // layer 8's epilogue arrives on a_ready[0..3] with nobody waiting: consume the phases
+        for (int q = 0; q < 4; ++q) { wait_bar(&s.a_ready[q], (ph_a >> q) & 1); ph_a ^= 1u << q; }
+      } else {
+        // the next slot's layer 1 overwrites D[0,128): wait until the dir-layer epilogue has read it
+        wait_bar(&s.d_drained, ph_drain); ph_drain ^= 1;
       }
     }
   } else {
@@ -508,73 +541,99 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     // hand-off to the MMA issuer, which lives in the leader CTA
     auto signal = [&](uint64_t* bar) { if (kCg == 2 && !leader) mbar_arrive_remote(bar, 0); else mbar_arrive(bar); };
-    uint32_t ph_d[2] = {0, 0};
-    for (long long slot = 0; slot < n_slots; ++slot) {
-      const long long tile = (group + slot * n_groups) * kCg + cta_rank;
-      const long long p0 = tile * kTile;
-      const long long pt = p0 + row;
-      // ---------------- prologue: positional encodings -> smem (canonical, hi/lo)
-      {
-        auto put = [&](unsigned char (*dst)[kTile * kXyzPad * 2], int k, float v) {
-          uint16_t hi, lo;
-          if (kSplit) split16<kBf16>(v, hi, lo); else { hi = cvt16<kBf16>(v); lo = 0; }
-          *reinterpret_cast<uint16_t*>(dst[0] + canon_off(row, k)) = hi;
-          if (kSplit) *reinterpret_cast<uint16_t*>(dst[kSplit ? 1 : 0] + canon_off(row, k)) = lo;
-        };
-        auto put_dir = [&](int k, float v) {
-          uint16_t hi, lo;
-          if (kSplit) split16<kBf16>(v, hi, lo); else { hi = cvt16<kBf16>(v); lo = 0; }
-          *reinterpret_cast<uint16_t*>(s.dir[0] + canon_off(row, k)) = hi;
-          if (kSplit) *reinterpret_cast<uint16_t*>(s.dir[kSplit ? 1 : 0] + canon_off(row, k)) = lo;
-        };
-        if (kEmbedded) {
-          const int nin = p.sigma_only ? kXyzCh : kXyzCh + kDirCh;
-          const float* xr = p.x + pt * p.x_stride;
-          for (int k = ch * 32; k < ch * 32 + 32; ++k)
-            put(s.enc, k, (pt < p.n_points && k < kXyzCh) ? xr[k] : 0.f);
-          for (int k = ch * 16; k < ch * 16 + 16; ++k)
-            put_dir(k, (pt < p.n_points && k < kDirCh && kXyzCh + k < nin) ? xr[kXyzCh + k] : 0.f);
-        } else {
-          float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, zz = 0.f;
-          if (pt < p.n_points) {
-            const long long ray = pt / p.n_samples;
-            const float4 r0 = *reinterpret_cast<const float4*>(p.rays + ray * 8);
-            const float4 r1 = *reinterpret_cast<const float4*>(p.rays + ray * 8 + 4);
-            o[0] = r0.x; o[1] = r0.y; o[2] = r0.z;
-            d[0] = r0.w; d[1] = r1.x; d[2] = r1.y;
-            zz = p.z[pt];
-          }
+    uint32_t ph_d[2] = {0, 0}, ph_free = 0;
+
+    // ---- positional encodings of one tile -> smem (canonical, hi/lo).  Split in pieces so they
+    // fit the epilogue warps' idle windows: xyz part 0 (identity + 3 of this thread's 5
+    // frequencies), xyz part 1 (the other 2 + zero pad), and the direction embedding.
+    auto put_enc = [&](int k, float v) {
+      uint16_t hi, lo;
+      if (kSplit) split16<kBf16>(v, hi, lo); else { hi = cvt16<kBf16>(v); lo = 0; }
+      *reinterpret_cast<uint16_t*>(s.enc[0] + canon_off(row, k)) = hi;
+      if (kSplit) *reinterpret_cast<uint16_t*>(s.enc[kSplit ? 1 : 0] + canon_off(row, k)) = lo;
+    };
+    auto put_dir = [&](int k, float v) {
+      uint16_t hi, lo;
+      if (kSplit) split16<kBf16>(v, hi, lo); else { hi = cvt16<kBf16>(v); lo = 0; }
+      *reinterpret_cast<uint16_t*>(s.dir[0] + canon_off(row, k)) = hi;
+      if (kSplit) *reinterpret_cast<uint16_t*>(s.dir[kSplit ? 1 : 0] + canon_off(row, k)) = lo;
+    };
+    auto tile_of = [&](long long slot) { return (group + slot * n_groups) * kCg + cta_rank; };
+    auto encode_xyz = [&](long long slot, int part) {
+      const long long pt = tile_of(slot) * kTile + row;
+      if (kEmbedded) {
+        const float* xr = p.x + pt * p.x_stride;
+        for (int k = ch * 32 + part * 16; k < ch * 32 + part * 16 + 16; ++k)
+          put_enc(k, (pt < p.n_points && k < kXyzCh) ? xr[k] : 0.f);
+      } else {
+        float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, zz = 0.f;
+        if (pt < p.n_points) {
+          const long long ray = pt / p.n_samples;
+          const float4 r0 = *reinterpret_cast<const float4*>(p.rays + ray * 8);
+          const float4 r1 = *reinterpret_cast<const float4*>(p.rays + ray * 8 + 4);
+          o[0] = r0.x; o[1] = r0.y; o[2] = r0.z;
+          d[0] = r0.w; d[1] = r1.x; d[2] = r1.y;
+          zz = p.z[pt];
+        }
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float x = __fadd_rn(o[c], __fmul_rn(d[c], zz));   // rendering.py:284-285 rounding
-            if (ch == 0) { put(s.enc, c, x); put_dir(c, d[c]); }
-#pragma unroll
-            for (int f = 0; f < 5; ++f) {
-              const int fr = ch * 5 + f;
-              float sn, cs;
-              sincosf(x * (float)(1 << fr), &sn, &cs);
-              put(s.enc, 3 + fr * 6 + c, sn);
-              put(s.enc, 3 + fr * 6 + 3 + c, cs);
-            }
-#pragma unroll
-            for (int f = 0; f < 2; ++f) {
-              const int fr = ch * 2 + f;
-              float sn, cs;
-              sincosf(d[c] * (float)(1 << fr), &sn, &cs);
-              put_dir(3 + fr * 6 + c, sn);
-              put_dir(3 + fr * 6 + 3 + c, cs);
-            }
-          }
-          if (ch == 1) {
-            put(s.enc, kXyzCh, 0.f);
-#pragma unroll
-            for (int k = kDirCh; k < kDirPad; ++k) put_dir(k, 0.f);
+        for (int c = 0; c < 3; ++c) {
+          const float x = __fadd_rn(o[c], __fmul_rn(d[c], zz));   // rendering.py:284-285 rounding
+          if (part == 0 && ch == 0) put_enc(c, x);
+          const int f0 = part == 0 ? 0 : 3, f1 = part == 0 ? 3 : 5;
+          for (int f = f0; f < f1; ++f) {
+            const int fr = ch * 5 + f;
+            float sn, cs;
+            sincosf(x * (float)(1 << fr), &sn, &cs);
+            put_enc(3 + fr * 6 + c, sn);
+            put_enc(3 + fr * 6 + 3 + c, cs);
           }
         }
+        if (part == 1 && ch == 1) put_enc(kXyzCh, 0.f);
+      }
+      if (part == 1) {
         fence_proxy_async_smem();     // generic-proxy smem writes -> visible to tcgen05.mma
         signal(&s.enc_ready);
       }
+    };
+    auto encode_dir = [&](long long slot) {
+      const long long pt = tile_of(slot) * kTile + row;
+      if (kEmbedded) {
+        const int nin = p.sigma_only ? kXyzCh : kXyzCh + kDirCh;
+        const float* xr = p.x + pt * p.x_stride;
+        for (int k = ch * 16; k < ch * 16 + 16; ++k)
+          put_dir(k, (pt < p.n_points && k < kDirCh && kXyzCh + k < nin) ? xr[kXyzCh + k] : 0.f);
+      } else {
+        float d[3] = {0.f, 0.f, 0.f};
+        if (pt < p.n_points) {
+          const long long ray = pt / p.n_samples;
+          d[0] = p.rays[ray * 8 + 3]; d[1] = p.rays[ray * 8 + 4]; d[2] = p.rays[ray * 8 + 5];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (ch == 0) put_dir(c, d[c]);
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            const int fr = ch * 2 + f;
+            float sn, cs;
+            sincosf(d[c] * (float)(1 << fr), &sn, &cs);
+            put_dir(3 + fr * 6 + c, sn);
+            put_dir(3 + fr * 6 + 3 + c, cs);
+          }
+        }
+        if (ch == 1) {
+#pragma unroll
+          for (int k = kDirCh; k < kDirPad; ++k) put_dir(k, 0.f);
+        }
+      }
+      fence_proxy_async_smem();
+      signal(&s.dir_ready);
+    };
 
+    // first slot: nothing to hide behind
+    if (n_slots > 0) { encode_xyz(0, 0); encode_xyz(0, 1); }
+
+    for (long long slot = 0; slot < n_slots; ++slot) {
+      const long long pt = tile_of(slot) * kTile + row;
       float sig_part = 0.f;
       // ---------------- trunk + bottleneck epilogues: D (TMEM) -> act -> A (TMEM)
       for (int l = 0; l < n_layers_epi; ++l) {
@@ -582,34 +641,77 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
         const bool relu = l < 8;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
+          const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3 && tid == 0;
+          const int tb = 1024 + (l * 2 + h) * 8;
+          trace(tr, tb + 0);
           mbar_wait(&s.d_full[h], ph_d[h]); ph_d[h] ^= 1;
           tc_fence_after();
-#pragma unroll 1
-          for (int g = 0; g < 2; ++g) {
-            if (p.debug & 2) break;
-            const int c0 = h * kNh + ch * 64 + g * 32;   // output columns == next layer's k
-            uint32_t v[32];
-            tmem_ld32(tbase + lane_base + kColD + c0, v);
-            tmem_wait_ld();
+          trace(tr, tb + 1);
+          if (p.debug & 2) {
+            if (h == 0) { mbar_wait(&s.a_free, ph_free); ph_free ^= 1; }
+            tc_fence_before(); signal(&s.a_ready[h * 2]); signal(&s.a_ready[h * 2 + 1]); continue;
+          }
+          // drain this accumulator half into registers (both 64-column quarters), then finish the
+          // quarters one at a time so the next layer's first K chunks can start early
+          uint32_t v[2][32];
+          tmem_ld32(tbase + lane_base + kColD + h * kNh + ch * 32, v[0]);
+          tmem_ld32(tbase + lane_base + kColD + h * kNh + 64 + ch * 32, v[1]);
+          tmem_wait_ld();
+          trace(tr, tb + 2);
+          // bias + activation + hi/lo split of one 32-column group, in place: v[2j] = hi pair j,
+          // v[2j+1] = lo pair j (columns c0+2j, c0+2j+1)
+          auto finish_group = [&](uint32_t (&vv)[32], int c0, auto relu_tag, auto sigma_tag) {
+            constexpr bool kRelu = decltype(relu_tag)::value, kSigma = decltype(sigma_tag)::value;
+            const float2* b2 = reinterpret_cast<const float2*>(bias + c0);
+            const float2* w2 = reinterpret_cast<const float2*>(s.cst + CL.sigma_w + c0);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 bb = b2[j];
+              float x0 = __uint_as_float(vv[2 * j]) + bb.x;
+              float x1 = __uint_as_float(vv[2 * j + 1]) + bb.y;
+              if (kRelu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              if (kSigma) { const float2 ww = w2[j]; sig_part = fmaf(x0, ww.x, sig_part); sig_part = fmaf(x1, ww.y, sig_part); }
+              split_pair<kBf16, kSplit, kRelu>(x0, x1, vv[2 * j], vv[2 * j + 1]);
+            }
+          };
+          auto finish = [&](uint32_t (&vv)[32], int c0) {
+            if (l == 7) finish_group(vv, c0, std::true_type{}, std::true_type{});
+            else if (relu) finish_group(vv, c0, std::true_type{}, std::false_type{});
+            else finish_group(vv, c0, std::false_type{}, std::false_type{});
+          };
+          auto store_group = [&](uint32_t (&vv)[32], int c0, int q) {
             uint32_t phi[16], plo[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float x0 = __uint_as_float(v[j]) + bias[c0 + j];
-              float x1 = __uint_as_float(v[j + 1]) + bias[c0 + j + 1];
-              if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-              if (l == 7) {
-                sig_part = fmaf(x0, s.cst[CL.sigma_w + c0 + j], sig_part);
-                sig_part = fmaf(x1, s.cst[CL.sigma_w + c0 + j + 1], sig_part);
-              }
-              split_pair<kBf16, kSplit>(x0, x1, phi[j >> 1], plo[j >> 1]);
-            }
+            for (int j = 0; j < 16; ++j) { phi[j] = vv[2 * j]; plo[j] = vv[2 * j + 1]; }
             tmem_st16(tbase + lane_base + kColAhi + (c0 >> 1), phi);
             if (kSplit) tmem_st16(tbase + lane_base + kColAlo + (c0 >> 1), plo);
+            tmem_wait_st();
+            tc_fence_before();
+            signal(&s.a_ready[h * 2 + q]);
+            trace(tr, tb + 3 + q);
+          };
+          const int c00 = h * kNh + ch * 32, c01 = h * kNh + 64 + ch * 32;   // output columns == next layer's k
+          if (h == 0) {
+            // half a's results go to A[k 0..127], which this layer's (b,k0) MMAs still read: finish
+            // the math now (it overlaps both b phases), hold the stores until they have retired
+            finish(v[0], c00);
+            finish(v[1], c01);
+            mbar_wait(&s.a_free, ph_free); ph_free ^= 1;
+            tc_fence_after();
+            store_group(v[0], c00, 0);
+            store_group(v[1], c01, 1);
+          } else {
+            // half b's target A[k 128..255] is idle: deliver each quarter as soon as it is done
+            finish(v[0], c00);
+            store_group(v[0], c00, 0);
+            finish(v[1], c01);
+            store_group(v[1], c01, 1);
           }
-          tmem_wait_st();
-          tc_fence_before();
-          signal(&s.a_ready[h]);
         }
+        // ---- background work in the idle window before this layer's next accumulator half is ready
+        if (l == 0 && !p.sigma_only) encode_dir(slot);                       // dir layer of THIS slot
+        if (l == 5 && slot + 1 < n_slots) encode_xyz(slot + 1, 0);            // enc is free once layer 5's
+        if (l == 6 && slot + 1 < n_slots) encode_xyz(slot + 1, 1);            // (skip) MMAs have retired
         if (l == 7) {
           // sigma head (nerf.py:136): combine the two column halves of each row
           s.part[ch][0][row] = sig_part;
@@ -626,26 +728,46 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 
       // ---------------- direction layer epilogue + rgb head + output
       {
+        const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3 && tid == 0;
+        const int tb = 1024 + 18 * 8;
+        trace(tr, tb + 0);
         mbar_wait(&s.d_full[0], ph_d[0]); ph_d[0] ^= 1;
         tc_fence_after();
+        trace(tr, tb + 1);
         const float* bias = s.cst + CL.b[9];
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll 1
-        for (int g = 0; g < 2; ++g) {
-          const int c0 = ch * 64 + g * 32;
-          uint32_t v[32];
-          tmem_ld32(tbase + lane_base + kColD + c0, v);
-          tmem_wait_ld();
+        uint32_t v[2][32];
+        tmem_ld32(tbase + lane_base + kColD + ch * 32, v[0]);
+        tmem_ld32(tbase + lane_base + kColD + 64 + ch * 32, v[1]);
+        tmem_wait_ld();
+        tc_fence_before();
+        signal(&s.d_drained);      // D[0,128) is in registers: the next slot's layer 1 may overwrite it
+        trace(tr, tb + 2);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) + bias[c0 + j];
-            x = new_activation ? shifted_softplus_f(x) : fmaxf(x, 0.f);
-            a0 = fmaf(x, s.cst[CL.rgb_w + c0 + j], a0);
-            a1 = fmaf(x, s.cst[CL.rgb_w + kHalf + c0 + j], a1);
-            a2 = fmaf(x, s.cst[CL.rgb_w + 2 * kHalf + c0 + j], a2);
+        for (int g = 0; g < 2; ++g) {
+          const int c0 = g * 64 + ch * 32;
+          const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+          const float4* w0 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + c0);
+          const float4* w1 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + kHalf + c0);
+          const float4* w2 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + 2 * kHalf + c0);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[j4], r0 = w0[j4], r1 = w1[j4], r2 = w2[j4];
+            float x[4] = {__uint_as_float(v[g][4 * j4]) + bb.x, __uint_as_float(v[g][4 * j4 + 1]) + bb.y,
+                          __uint_as_float(v[g][4 * j4 + 2]) + bb.z, __uint_as_float(v[g][4 * j4 + 3]) + bb.w};
+            if (new_activation) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = shifted_softplus_fast(x[e]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+            }
+            a0 = fmaf(x[0], r0.x, a0); a0 = fmaf(x[1], r0.y, a0); a0 = fmaf(x[2], r0.z, a0); a0 = fmaf(x[3], r0.w, a0);
+            a1 = fmaf(x[0], r1.x, a1); a1 = fmaf(x[1], r1.y, a1); a1 = fmaf(x[2], r1.z, a1); a1 = fmaf(x[3], r1.w, a1);
+            a2 = fmaf(x[0], r2.x, a2); a2 = fmaf(x[1], r2.y, a2); a2 = fmaf(x[2], r2.z, a2); a2 = fmaf(x[3], r2.w, a2);
           }
         }
-        tc_fence_before();
+        trace(tr, tb + 3);
         s.part[ch][1][row] = a0; s.part[ch][2][row] = a1; s.part[ch][3][row] = a2;
         epi_bar_sync();
         if (ch == 0 && pt < p.n_points) {
@@ -658,6 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           reinterpret_cast<float4*>(p.out)[pt] = make_float4(c[0], c[1], c[2], s.part[0][0][row]);
         }
         epi_bar_sync();
+        trace(tr, tb + 4);
       }
     }
   }
@@ -743,3 +866,9 @@ int mlp_forward_tc(const void* packed, int precision, const float* x, int64_t x_
 }
 
 }  // namespace snb
+
+// debug-only export (not part of the public header): copy the device trace buffer to the host
+extern "C" int snb_debug_trace(long long* host_out, int n) {
+  if (n > snb::kTraceLen) n = snb::kTraceLen;
+  return cudaMemcpyFromSymbol(host_out, snb::g_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}

@@ -174,6 +174,104 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(
 }
 
 // ---------------------------------------------------------------------------------------
+// composite_bwd: closed-form backward of the compositing (checked against
+// autograd through the oracle in tests/test_gpu_backward.py).  One warp per ray; alpha, T, w are
+// recomputed from sigma and z (nothing saved by the forward), the suffix sum
+// sum_{k>i} gw_k w_k is a reverse warp scan.
+//   gw_i     = g_rgb . c_i + g_depth z_i + g_w_i - [white_back] sum_c g_rgb_c
+//   galpha_i = gw_i T_i - (sum_{k>i} gw_k w_k) / (1 - alpha_i + 1e-10)
+//   gsigma_i = galpha_i delta_i exp(-delta_i relu(s_i)) [s_i > 0],   s_i = sigma_i + noise_i
+//   gc_i     = g_rgb w_i
+// Algorithmic bytes: 16+4(+4) in, 16 out per point (+4 if g_w is given).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) composite_bwd_kernel(
+    const float* __restrict__ raw, const float* __restrict__ z_vals, const float* __restrict__ rays,
+    const float* __restrict__ noise, float noise_std, int white_back, const float* __restrict__ g_rgb,
+    const float* __restrict__ g_depth, const float* __restrict__ g_w, long long n_rays, int S,
+    float* __restrict__ g_raw) {
+  extern __shared__ float sm[];   // per warp: alpha[S], T[S], gwv[S] (= gw_i * w_i, then its suffix sums)
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* sa = sm + (size_t)wib * 3 * S;
+  float* sT = sa + S;
+  float* sg = sT + S;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long ray = warp; ray < n_rays; ray += nwarps) {
+    const float dx = rays[ray * 8 + 3], dy = rays[ray * 8 + 4], dz = rays[ray * 8 + 5];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float* zr = z_vals + ray * S;
+    float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f;
+    if (g_rgb != nullptr) { gr = g_rgb[ray * 3]; gg = g_rgb[ray * 3 + 1]; gb = g_rgb[ray * 3 + 2]; }
+    if (g_depth != nullptr) gd = g_depth[ray];
+    const float gwb = white_back ? (gr + gg + gb) : 0.f;
+    // forward recompute + gw_i w_i
+    float carry = 1.0f;
+    for (int base = 0; base < S; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < S;
+      float alpha = 0.f, t = 1.0f, gw = 0.f;
+      if (valid) {
+        const float4 v = reinterpret_cast<const float4*>(raw)[ray * S + i];
+        const float z = zr[i];
+        float delta = (i + 1 < S) ? __fsub_rn(zr[i + 1], z) : 1e10f;
+        delta = __fmul_rn(delta, dnorm);
+        float sgm = v.w;
+        if (noise != nullptr) sgm = __fadd_rn(sgm, __fmul_rn(noise[ray * S + i], noise_std));
+        alpha = __fsub_rn(1.0f, expf(-__fmul_rn(delta, fmaxf(sgm, 0.f))));
+        t = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+        gw = gr * v.x + gg * v.y + gb * v.z + gd * z - gwb;
+        if (g_w != nullptr) gw += g_w[ray * S + i];
+      }
+      float scan = t;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const float up = __shfl_up_sync(kFull, scan, off);
+        if (lane >= off) scan *= up;
+      }
+      float excl = __shfl_up_sync(kFull, scan, 1);
+      if (lane == 0) excl = 1.0f;
+      const float T = carry * excl;
+      carry *= __shfl_sync(kFull, scan, 31);
+      if (valid) { sa[i] = alpha; sT[i] = T; sg[i] = gw * alpha * T; }
+    }
+    __syncwarp();
+    // exclusive suffix sums of gw_k w_k, walking the 32-sample groups backwards
+    float tail = 0.f;
+    for (int base = ((S - 1) / 32) * 32; base >= 0; base -= 32) {
+      const int i = base + lane;
+      const float v = i < S ? sg[i] : 0.f;
+      float scan = v;  // inclusive suffix scan inside the group
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const float dn = __shfl_down_sync(kFull, scan, off);
+        if (lane + off < 32) scan += dn;
+      }
+      const float group_total = __shfl_sync(kFull, scan, 0);
+      if (i < S) sg[i] = tail + scan - v;   // sum over k > i
+      tail += group_total;
+    }
+    __syncwarp();
+    for (int i = lane; i < S; i += 32) {
+      const float4 v = reinterpret_cast<const float4*>(raw)[ray * S + i];
+      const float z = zr[i];
+      float delta = (i + 1 < S) ? __fsub_rn(zr[i + 1], z) : 1e10f;
+      delta = __fmul_rn(delta, dnorm);
+      float sgm = v.w;
+      if (noise != nullptr) sgm = __fadd_rn(sgm, __fmul_rn(noise[ray * S + i], noise_std));
+      const float alpha = sa[i], T = sT[i];
+      const float w = alpha * T;
+      float gw = gr * v.x + gg * v.y + gb * v.z + gd * z - gwb;
+      if (g_w != nullptr) gw += g_w[ray * S + i];
+      const float galpha = gw * T - sg[i] / (__fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+      const float e = expf(-__fmul_rn(delta, fmaxf(sgm, 0.f)));
+      const float gsig = sgm > 0.f ? galpha * delta * e : 0.f;
+      reinterpret_cast<float4*>(g_raw)[ray * S + i] = make_float4(gr * w, gg * w, gb * w, gsig);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // inverse-CDF sampling.  One warp per ray; cdf (M+1 floats) and, for the merged variant, the
 // S+Ni depths live in the warp's slice of shared memory.
 //   sample_pdf:       in 4*(M + M+1) B/ray (+4*Ni u), out 4*Ni B/ray
@@ -373,6 +471,24 @@ int launch_composite(const float* raw, int raw_channels, const float* z, const f
   composite_fwd_kernel<<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays,
                                              S, rgb, depth, w);
   return check_launch("composite_fwd_kernel");
+}
+
+int launch_composite_bwd(const float* raw, const float* z, const float* rays, const float* noise, float noise_std,
+                          int white_back, const float* g_rgb, const float* g_depth, const float* g_w, int64_t n_rays,
+                          int S, float* g_raw, cudaStream_t st) {
+  if (n_rays == 0) return SNB_OK;
+  const size_t smem = (size_t)8 * 3 * S * sizeof(float);
+  if (smem > 96 * 1024) return fail(SNB_ERR_UNSUPPORTED, "snb_composite_backward: too many samples per ray (%d)", S);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(composite_bwd): %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  const int grid = grid_for(n_rays, 8, device_sms() * 8);
+  composite_bwd_kernel<<<grid, 256, smem, st>>>(raw, z, rays, noise, noise_std, white_back, g_rgb, g_depth, g_w,
+                                                n_rays, S, g_raw);
+  return check_launch("composite_bwd_kernel");
 }
 
 int launch_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride,

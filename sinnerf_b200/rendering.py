@@ -39,6 +39,141 @@ def _linspace01(n: int, device) -> torch.Tensor:
     return t
 
 
+# --------------------------------------------------------------------------- training path
+class _FieldPass(torch.autograd.Function):
+    """raw (N,S,4) = field(rays, z; params).  Forward keeps the activations (snb_field_forward_train),
+    backward = snb_field_backward.  Differentiable in the 24 parameter tensors only -- the
+    reference propagates nothing into rays / z either (rendering.py:311-313)."""
+
+    @staticmethod
+    def forward(ctx, model: "NeRF", rays, z, *params):
+        lib = _lib.load()
+        dev = rays.device
+        n, S = z.shape
+        P = n * S
+        img = model.packed_weights("fp32")
+        raw = torch.empty(n, S, 4, device=dev, dtype=torch.float32)
+        save_enc = torch.empty(P, 64, device=dev, dtype=torch.float32)
+        save_dir = torch.empty(P, 32, device=dev, dtype=torch.float32)
+        save_h = torch.empty(9, P, 256, device=dev, dtype=torch.float32)
+        save_g = torch.empty(P, 128, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.snb_field_forward_train(_lib.ptr(img), _lib.ptr(rays), _lib.ptr(z), n, S, _lib.ptr(raw),
+                                                   _lib.ptr(save_enc), _lib.ptr(save_dir), _lib.ptr(save_h),
+                                                   _lib.ptr(save_g), _lib.stream_ptr(dev)), "snb_field_forward_train")
+        ctx.save_for_backward(raw, save_enc, save_dir, save_h, save_g, *params)
+        ctx.new_activation = int(model.use_new_activation)
+        return raw
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        lib = _lib.load()
+        raw, save_enc, save_dir, save_h, save_g, *params = ctx.saved_tensors
+        dev = raw.device
+        P = raw.shape[0] * raw.shape[1]
+        g_raw = g_raw.contiguous().to(torch.float32)
+        ps = [p.detach().contiguous() for p in params]
+        grads = [torch.zeros_like(p) for p in ps]
+        ws_a = torch.empty(P, 256, device=dev, dtype=torch.float32)
+        ws_b = torch.empty(P, 256, device=dev, dtype=torch.float32)
+        ws_s = torch.empty(P, 128, device=dev, dtype=torch.float32)
+        parr = (C.c_void_p * 24)(*[p.data_ptr() for p in ps])
+        garr = (C.c_void_p * 24)(*[g.data_ptr() for g in grads])
+        with torch.cuda.device(dev):
+            _lib.check(lib.snb_field_backward(parr, garr, ctx.new_activation, _lib.ptr(g_raw), _lib.ptr(raw),
+                                              _lib.ptr(save_enc), _lib.ptr(save_dir), _lib.ptr(save_h),
+                                              _lib.ptr(save_g), P, _lib.ptr(ws_a), _lib.ptr(ws_b), _lib.ptr(ws_s),
+                                              _lib.stream_ptr(dev)), "snb_field_backward")
+        return (None, None, None, *grads)
+
+
+class _Composite(torch.autograd.Function):
+    """(rgb, depth, weights) = composite(raw, z, ...), backward = snb_composite_backward (closed form)."""
+
+    @staticmethod
+    def forward(ctx, raw, z, rays, noise, noise_std, white_back):
+        lib = _lib.load()
+        dev = raw.device
+        n, S = z.shape
+        rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        depth = torch.empty(n, device=dev, dtype=torch.float32)
+        w = torch.empty(n, S, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.snb_composite_forward(_lib.ptr(raw), 4, _lib.ptr(z), _lib.ptr(rays), _lib.ptr(noise),
+                                                 noise_std, int(white_back), n, S, _lib.ptr(rgb), _lib.ptr(depth),
+                                                 _lib.ptr(w), _lib.stream_ptr(dev)), "snb_composite_forward")
+        ctx.save_for_backward(raw, z, rays, noise if noise is not None else raw.new_empty(0))
+        ctx.cfg = (float(noise_std), int(white_back), noise is not None)
+        return rgb, depth, w
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_w):
+        lib = _lib.load()
+        raw, z, rays, noise = ctx.saved_tensors
+        noise_std, white_back, has_noise = ctx.cfg
+        dev = raw.device
+        n, S = z.shape
+        g_raw = torch.empty_like(raw)
+        keep = [t.contiguous().to(torch.float32) if t is not None else None for t in (g_rgb, g_depth, g_w)]
+        with torch.cuda.device(dev):
+            _lib.check(lib.snb_composite_backward(_lib.ptr(raw), _lib.ptr(z), _lib.ptr(rays),
+                                                  _lib.ptr(noise) if has_noise else None, noise_std, white_back,
+                                                  _lib.ptr(keep[0]), _lib.ptr(keep[1]), _lib.ptr(keep[2]), n, S,
+                                                  _lib.ptr(g_raw), _lib.stream_ptr(dev)), "snb_composite_backward")
+        return g_raw, None, None, None, None, None
+
+
+def _needs_grad(models) -> bool:
+    return torch.is_grad_enabled() and any(p.requires_grad for m in models for p in m.parameters())
+
+
+def _render_rays_train(models, r, S, Ni, use_disp, perturb, noise_std, white_back, detach_coarse, rng_draw):
+    """render_rays with autograd (reference models/rendering.py:126-335 under grad mode): same
+    kernels for sampling / importance sampling, the fp32 field pass that keeps activations, and
+    the closed-form compositing backward.  Gradients reach the NeRF parameters only."""
+    lib = _lib.load()
+    dev = r.device
+    n = r.shape[0]
+    st = _lib.stream_ptr(dev)
+
+    def new(*shape):
+        return torch.empty(*shape, device=dev, dtype=torch.float32)
+
+    perturb_u = rng_draw("perturb_u", torch.rand, n, S) if perturb > 0 else None
+    noise_c = rng_draw("noise_coarse", torch.randn, n, S) if (noise_std != 0 or DRAW_UNUSED_NOISE) else None
+    z_steps = _linspace01(S, dev)
+    z_c = new(n, S)
+    with torch.cuda.device(dev):
+        _lib.check(lib.snb_sample_coarse(_lib.ptr(r), _lib.ptr(z_steps), _lib.ptr(perturb_u), perturb, int(use_disp),
+                                         n, S, _lib.ptr(z_c), st), "snb_sample_coarse")
+
+    def field_pass(model, z, noise):
+        raw = _FieldPass.apply(model, r, z, *model._param_list())
+        return _Composite.apply(raw, z, r, noise if noise_std != 0 else None, noise_std, white_back)
+
+    if detach_coarse:
+        with torch.no_grad():
+            rgb_c, depth_c, w_c = field_pass(models[0], z_c, noise_c)
+    else:
+        rgb_c, depth_c, w_c = field_pass(models[0], z_c, noise_c)
+    result = {"rgb_coarse": rgb_c, "depth_coarse": depth_c, "opacity_coarse": w_c}
+    if Ni > 0:
+        det = not (perturb > 0)
+        pdf_u = None if det else rng_draw("pdf_u", torch.rand, n, Ni)
+        noise_f = rng_draw("noise_fine", torch.randn, n, S + Ni) if (noise_std != 0 or DRAW_UNUSED_NOISE) else None
+        u = _linspace01(Ni, dev) if det else pdf_u
+        z_f = new(n, S + Ni)
+        w_det = w_c.detach().contiguous()       # sample_pdf(...).detach(), rendering.py:311-313
+        with torch.cuda.device(dev):
+            _lib.check(lib.snb_importance_merge(_lib.ptr(z_c), _lib.ptr(w_det), _lib.ptr(u), 0 if det else Ni, n, S, Ni,
+                                                1e-5, _lib.ptr(z_f), None, st), "snb_importance_merge")
+        rgb_f, depth_f, w_f = field_pass(models[1], z_f, noise_f)
+        result["rgb_fine"], result["depth_fine"], result["opacity_fine"] = rgb_f, depth_f, w_f
+    else:
+        result["rgb_fine"], result["depth_fine"], result["opacity_fine"] = rgb_c, depth_c, w_c
+    return result
+
+
 def _as_rays(rays: torch.Tensor) -> torch.Tensor:
     _lib.require_device(rays, "render_rays")
     if rays.dim() != 2 or rays.shape[1] != 8:
@@ -102,7 +237,10 @@ def render_rays(models,
     models [coarse(, fine)] are sinnerf_b200.NeRF; embeddings [xyz, dir] must be the L=10 / L=4
     logscale embeddings SinNeRF builds (models/sinnerf.py:131-132) -- the kernels compute them
     on the fly, the modules are only inspected.  `chunk` is accepted and ignored: no (P,256)
-    activation ever reaches HBM, so there is nothing to chunk.  `noisy_coarse` is ignored exactly
+    activation ever reaches HBM in inference, so there is nothing to chunk.  Under autograd (grad
+    mode on and a model parameter requiring grad) the call runs the training path: fp32 field
+    pass that keeps activations + hand-written backward kernels; gradients reach the NeRF
+    parameters only, as in the reference.  `noisy_coarse` is ignored exactly
     as in the reference (:138).  Keyword-only extras: `precision` overrides
     sinnerf_b200.config; `_rng` injects the four random tensors (tests).
     """
@@ -134,6 +272,13 @@ def render_rays(models,
         if tuple(t.shape) != shape:
             raise ValueError(f"_rng['{name}'] must be {shape}, got {tuple(t.shape)}")
         return t.to(dev, torch.float32).contiguous()
+
+    if _needs_grad(models[:2 if Ni > 0 else 1]):
+        if test_time:
+            raise NotImplementedError("render_rays(test_time=True) under autograd is not built (the reference "
+                                      "never trains with it: models/sinnerf.py:176-186)")
+        return _render_rays_train(models, r, S, Ni, bool(use_disp), perturb, noise_std, bool(white_back),
+                                  bool(detach_coarse), rnd)
 
     # random draws in the reference's order (rendering.py:281, :224, :43, :224)
     perturb_u = rnd("perturb_u", torch.rand, n, S) if perturb > 0 else None

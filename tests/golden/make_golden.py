@@ -111,8 +111,39 @@ def render_case(name, models, rays, *, n_samples=64, n_importance=64, use_disp=F
     print("wrote", path, {k: v.shape for k, v in out.items() if k.startswith("out_")})
 
 
+def grad_golden(room):
+    """Reference autograd: d(loss)/d(params) for a fixed random projection of all outputs.
+    Stores per-tensor gradient norms and the full gradients of the small tensors."""
+    trained = [m.train() for m in room_models(room)]
+    rays = synthetic.random_rays("llff", 24, seed=5)
+    emb = [Embedding(3, 10), Embedding(3, 4)]
+    torch.manual_seed(4321)
+    res = render_rays(trained, emb, rays, 64, False, 1.0, 1.0, 64, 1024 * 32, False)
+    rng = replay_rng(4321, 24, 64, 64, 1.0)
+    g = torch.Generator().manual_seed(11)
+    proj = {k: torch.randn(v.shape, generator=g) for k, v in sorted(res.items())}
+    loss = sum((res[k] * proj[k]).sum() for k in sorted(res))
+    loss.backward()
+    out = {"rays": np_(rays), "loss": np.array(float(loss))}
+    for k, v in rng.items():
+        out["rng_" + k] = np_(v)
+    for k in sorted(proj):
+        out["proj_" + k] = np_(proj[k])
+    for which, m in (("coarse", trained[0]), ("fine", trained[1])):
+        for name, prm in m.named_parameters():
+            out[f"gnorm_{which}/{name}"] = np.array(float(prm.grad.norm()))
+            if prm.numel() <= 768:
+                out[f"grad_{which}/{name}"] = np_(prm.grad)
+    path = os.path.join(HERE, "grad_llff_room_train.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "loss", float(loss))
+
+
 def main():
     room = load_room()
+    if "--grad-only" in sys.argv:
+        grad_golden(room)
+        return
     np.savez_compressed(os.path.join(HERE, "room_weights.npz"), **room)
     print("room_weights:", len(room), "tensors")
 
@@ -184,6 +215,7 @@ def main():
     render_case("lego_room_testtime", trained, lego[:48], test_time=True, weights_tag="room")
     render_case("lego_seed0_32p16_odd", seed_models, lego[:33], n_samples=32, n_importance=16,
                 perturb=0.5, noise_std=0.3, white_back=True)
+    grad_golden(room)
 
 
 if __name__ == "__main__":

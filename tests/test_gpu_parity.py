@@ -283,7 +283,10 @@ def test_edge_cases():
     from sinnerf_b200.rendering import render_rays
     models = make_models(orc.default_init_params(0), orc.default_init_params(1))
     emb = embeddings()
-    out = render_rays(models, emb, torch.zeros(0, 8, device=DEV), 64, False, 0, 0, 64)
+    out = render_rays(models, emb, torch.zeros(0, 8, device=DEV), 64, False, 0, 0, 64)      # autograd path
+    assert out["rgb_fine"].shape == (0, 3) and out["opacity_fine"].shape == (0, 128)
+    with torch.no_grad():                                                                    # inference path
+        out = render_rays(models, emb, torch.zeros(0, 8, device=DEV), 64, False, 0, 0, 64)
     assert out["rgb_fine"].shape == (0, 3) and out["opacity_fine"].shape == (0, 128)
     with pytest.raises(UnboundLocalError):
         render_rays(models, emb, torch.zeros(4, 8, device=DEV), 64, test_time=True, N_importance=0)
@@ -291,7 +294,8 @@ def test_edge_cases():
         render_rays(models, emb, torch.zeros(4, 7, device=DEV))
     # a single ray, odd sample counts
     rays = torch.tensor([[0., 0., 4., 0.1, -0.2, -1., 2., 6.]], device=DEV)
-    o = render_rays(models, emb, rays, 17, False, 0, 0, 5)
+    with torch.no_grad():
+        o = render_rays(models, emb, rays, 17, False, 0, 0, 5)
     assert o["opacity_fine"].shape == (1, 22) and torch.isfinite(o["rgb_fine"]).all()
 
 
@@ -302,11 +306,14 @@ def test_rng_stream_matches_reference_order():
     models = make_models(room_params("coarse"), room_params("fine"))
     emb = embeddings()
     rays = t(load_npz("render_llff_room_64p64.npz")["rays"]).to(DEV)
-    torch.manual_seed(77)
-    a = render_rays(models, emb, rays, 64, False, 1.0, 1.0, 64)
-    torch.manual_seed(77)
-    n = rays.shape[0]
-    rng = {"perturb_u": torch.rand(n, 64, device=DEV), "noise_coarse": torch.randn(n, 64, device=DEV),
-           "pdf_u": torch.rand(n, 64, device=DEV), "noise_fine": torch.randn(n, 128, device=DEV)}
-    b = render_rays(models, emb, rays, 64, False, 1.0, 1.0, 64, _rng=rng)
+    for grad in (False, True):      # inference and autograd paths draw identically
+        with torch.set_grad_enabled(grad):
+            torch.manual_seed(77)
+            a = render_rays(models, emb, rays, 64, False, 1.0, 1.0, 64)
+            torch.manual_seed(77)
+            n = rays.shape[0]
+            rng = {"perturb_u": torch.rand(n, 64, device=DEV), "noise_coarse": torch.randn(n, 64, device=DEV),
+                   "pdf_u": torch.rand(n, 64, device=DEV), "noise_fine": torch.randn(n, 128, device=DEV)}
+            b = render_rays(models, emb, rays, 64, False, 1.0, 1.0, 64, _rng=rng)
+        assert torch.equal(a["rgb_fine"], b["rgb_fine"]) and torch.equal(a["opacity_fine"], b["opacity_fine"])
     assert torch.equal(a["rgb_fine"], b["rgb_fine"]) and torch.equal(a["opacity_fine"], b["opacity_fine"])

@@ -109,3 +109,23 @@ def test_properties_weights():
     case = load_npz("render_llff_room_64p64.npz")
     w = t(case["out_opacity_fine"])
     assert (w >= 0).all() and (w.sum(-1) <= 1 + 1e-5).all()
+
+
+def test_oracle_autograd_matches_reference_autograd():
+    """Gradients: autograd through the oracle == autograd through the reference (golden made by
+    tests/golden/make_golden.py::grad_golden), including the detach of the importance samples."""
+    gz = load_npz("grad_llff_room_train.npz")
+    pc = {k: v.clone().requires_grad_(True) for k, v in room_params("coarse").items()}
+    pf = {k: v.clone().requires_grad_(True) for k, v in room_params("fine").items()}
+    rng = {k[4:]: t(v) for k, v in gz.items() if k.startswith("rng_")}
+    out = orc.render_rays(pc, pf, t(gz["rays"]), N_samples=64, N_importance=64, perturb=1.0, noise_std=1.0, rng=rng)
+    loss = sum((out[k[5:]] * t(gz[k])).sum() for k in sorted(gz) if k.startswith("proj_"))
+    assert float(loss) == pytest.approx(float(gz["loss"]), rel=1e-5)
+    loss.backward()
+    for which, params in (("coarse", pc), ("fine", pf)):
+        for name, prm in params.items():
+            ref_norm = float(gz[f"gnorm_{which}/{name}"])
+            assert float(prm.grad.norm()) == pytest.approx(ref_norm, rel=2e-4, abs=1e-9), (which, name)
+            key = f"grad_{which}/{name}"
+            if key in gz:
+                assert_close(prm.grad, gz[key], 2e-4, key)
