@@ -254,11 +254,11 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
 
 // softplus(x - 1) with the hardware ex2 / lg2 approximations (abs error ~1e-7 on an O(1..200)
 // value; the accurate expf/log1pf pair cost the dir-layer epilogue ~10k cycles per tile).
-__device__ __forceinline__ float shifted_softplus_fast(float x) {
-  const float s = x - 1.0f;
-  const float t = __expf(-fabsf(s));                                   // (0, 1]
-  const float lp = t < 9.765625e-4f ? t * (1.0f - 0.5f * t) : __logf(1.0f + t);   // log1p(t)
-  return fmaxf(s, 0.0f) + lp;
+// `s` is already shifted (x - 1): 4 FP32 ops + 2 MUFU.
+__device__ __forceinline__ float softplus_fast(float s) {
+  float t;                                                             // exp(-|s|) in (0, 1]
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * fabsf(s)));
+  return fmaf(__log2f(1.0f + t), 0.6931471805599453f, fmaxf(s, 0.0f));   // max(s,0) + log1p(t)  (lg2.approx)
 }
 
 // ------------------------------------------------------------------ pack kernel
@@ -753,11 +753,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bb = b4[j4], r0 = w0[j4], r1 = w1[j4], r2 = w2[j4];
-            float x[4] = {__uint_as_float(v[g][4 * j4]) + bb.x, __uint_as_float(v[g][4 * j4 + 1]) + bb.y,
-                          __uint_as_float(v[g][4 * j4 + 2]) + bb.z, __uint_as_float(v[g][4 * j4 + 3]) + bb.w};
+            // shifted softplus: fold the -1 into the bias
+            const float sh = new_activation ? 1.0f : 0.0f;
+            float x[4] = {__uint_as_float(v[g][4 * j4]) + (bb.x - sh), __uint_as_float(v[g][4 * j4 + 1]) + (bb.y - sh),
+                          __uint_as_float(v[g][4 * j4 + 2]) + (bb.z - sh), __uint_as_float(v[g][4 * j4 + 3]) + (bb.w - sh)};
             if (new_activation) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] = shifted_softplus_fast(x[e]);
+              for (int e = 0; e < 4; ++e) x[e] = softplus_fast(x[e]);
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);

@@ -127,7 +127,8 @@ def _needs_grad(models) -> bool:
     return torch.is_grad_enabled() and any(p.requires_grad for m in models for p in m.parameters())
 
 
-def _render_rays_train(models, r, S, Ni, use_disp, perturb, noise_std, white_back, detach_coarse, rng_draw):
+def _render_rays_train(models, r, S, Ni, use_disp, perturb, noise_std, white_back, detach_coarse, rng_draw,
+                       return_intermediates=False):
     """render_rays with autograd (reference models/rendering.py:126-335 under grad mode): same
     kernels for sampling / importance sampling, the fp32 field pass that keeps activations, and
     the closed-form compositing backward.  Gradients reach the NeRF parameters only."""
@@ -170,7 +171,10 @@ def _render_rays_train(models, r, S, Ni, use_disp, perturb, noise_std, white_bac
         rgb_f, depth_f, w_f = field_pass(models[1], z_f, noise_f)
         result["rgb_fine"], result["depth_fine"], result["opacity_fine"] = rgb_f, depth_f, w_f
     else:
+        z_f = None
         result["rgb_fine"], result["depth_fine"], result["opacity_fine"] = rgb_c, depth_c, w_c
+    if return_intermediates:
+        result["_inter"] = {"z_coarse": z_c, "z_fine": z_f}
     return result
 
 
@@ -278,7 +282,7 @@ def render_rays(models,
             raise NotImplementedError("render_rays(test_time=True) under autograd is not built (the reference "
                                       "never trains with it: models/sinnerf.py:176-186)")
         return _render_rays_train(models, r, S, Ni, bool(use_disp), perturb, noise_std, bool(white_back),
-                                  bool(detach_coarse), rnd)
+                                  bool(detach_coarse), rnd, _return_intermediates)
 
     # random draws in the reference's order (rendering.py:281, :224, :43, :224)
     perturb_u = rnd("perturb_u", torch.rand, n, S) if perturb > 0 else None

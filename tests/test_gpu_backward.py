@@ -65,21 +65,25 @@ def test_render_rays_gradients_match_oracle_autograd(weights, train_noise):
     else:
         pc, pf = orc.default_init_params(0), orc.default_init_params(1)
     perturb, noise_std = (1.0, 1.0) if train_noise else (0.0, 0.0)
-    # oracle + autograd on CPU
-    oc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
-    of = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
-    ref = orc.render_rays(oc, of, rays, N_samples=64, N_importance=64, perturb=perturb, noise_std=noise_std, rng=rng)
-    proj = make_proj(ref, 5)
-    loss_of(ref, proj).backward()
-    # CUDA path
+    # CUDA path first: its fine-pass depths are then injected into the oracle, so the comparison is
+    # stage-wise (the importance sampling is chaotic in the last bits of the coarse weights; SURVEY
+    # hard part 3) and both sides differentiate the same function
     models = []
     for p in (pc, pf):
         m = NeRF(use_new_activation=True)
         m.load_state_dict(p)
         models.append(m.to(DEV))
     out = render_rays(models, [Embedding(3, 10), Embedding(3, 4)], rays.to(DEV), 64, False, perturb, noise_std, 64,
-                      _rng={k: v.to(DEV) for k, v in rng.items()})
-    for k in ("rgb_fine", "depth_fine", "rgb_coarse", "opacity_coarse"):
+                      _rng={k: v.to(DEV) for k, v in rng.items()}, _return_intermediates=True)
+    z_f = out["_inter"]["z_fine"].detach().cpu()
+    # oracle + autograd on CPU
+    oc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    of = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+    ref = orc.render_rays(oc, of, rays, N_samples=64, N_importance=64, perturb=perturb, noise_std=noise_std, rng=rng,
+                          z_fine_override=z_f)
+    proj = make_proj(ref, 5)
+    loss_of(ref, proj).backward()
+    for k in ("rgb_fine", "depth_fine", "opacity_fine", "rgb_coarse", "opacity_coarse"):
         assert rel_l2(out[k].detach().cpu(), ref[k].detach()) <= 1e-4, k
     loss_of(out, proj).backward()
     for name, ref_params, model in (("coarse", oc, models[0]), ("fine", of, models[1])):
@@ -90,10 +94,7 @@ def test_render_rays_gradients_match_oracle_autograd(weights, train_noise):
             if float(v.grad.norm()) == 0.0:
                 assert float(got.norm()) == 0.0, (name, k)
                 continue
-            # the fine pass sees slightly different sample depths than the oracle (chaotic
-            # importance sampling), which perturbs its gradients more than the coarse ones
-            tol = 1e-3 if name == "coarse" else 5e-3
-            assert rel_l2(got.cpu(), v.grad) <= tol, (name, k, rel_l2(got.cpu(), v.grad))
+            assert rel_l2(got.cpu(), v.grad) <= 1e-3, (name, k, rel_l2(got.cpu(), v.grad))
 
 
 def test_detach_coarse_and_no_grad_paths():
