@@ -53,20 +53,17 @@ constexpr int kNh = 128;               // output columns per MMA (N); a 256-wide
 constexpr int kEpiWarps = 8;           // warps 0..7: prologue / epilogue (2 per TMEM lane quadrant)
 constexpr int kMmaWarp = 8, kLoadWarp = 9;
 constexpr int kThreads = 320;
-#ifndef SNB_TC_STAGES
-#define SNB_TC_STAGES 10
-#endif
-constexpr int kStages = SNB_TC_STAGES;
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
 
-// per cta_group geometry: a chunk is 128 output rows x kKc of K; each CTA of the group holds
-// kRowsB = 128 / cg of those rows, so a CTA's ring stage is kRowsB * kKc * 2 B (x2 with lo)
+// per cta_group geometry: a chunk is 128 output rows x (16 * steps) of K, steps <= kMaxSteps; each
+// CTA of the group holds kRowsB = 128 / cg of those rows
 template <int kCg>
 struct Geo {
-  static constexpr int kKc = kCg == 2 ? 64 : 32;
+  static constexpr int kKc = kCg == 2 ? 128 : 32;            // K per full chunk
   static constexpr int kRowsB = kNh / kCg;
-  static constexpr int kSteps = kKc / 16;
-  static constexpr uint32_t kPartBytes = kRowsB * kKc * 2;   // one of {hi, lo} of a CTA's share
+  static constexpr int kMaxSteps = kKc / 16;
+  static constexpr uint32_t kStepBytes = kRowsB * 16 * 2;    // one K16 step of one of {hi, lo} of a CTA's share
+  static constexpr uint32_t kPartBytesMax = kStepBytes * kMaxSteps;
 };
 
 enum { SRC_ENC = 0, SRC_HID = 1, SRC_DIR = 2 };
@@ -75,103 +72,91 @@ enum { SRC_ENC = 0, SRC_HID = 1, SRC_DIR = 2 };
 enum { WAIT_NONE = 0, WAIT_ENC = 1, WAIT_DIR = 2, WAIT_A0 = 4, WAIT_A1 = 5, WAIT_A2 = 6, WAIT_A3 = 7 };
 enum { COMMIT_NONE = 0, COMMIT_D0 = 1, COMMIT_D1 = 2, COMMIT_AFREE = 4 };   // bit flags
 
-struct Chunk {
-  uint8_t layer;   // 0..9 (8 = bottleneck, 9 = direction layer)
-  uint8_t half;    // output columns [128*half, +128)
-  uint8_t src;     // SRC_*: where the A operand of this chunk lives
-  uint8_t kc;      // chunk index inside that source (K offset = kKc*kc)
-  uint8_t kpad;    // chunk index in the layer's padded K space (gemm_k)
-  uint8_t first;   // first chunk of this (layer, half): accumulate = 0
-  uint8_t wait;    // WAIT_* before issuing (low nibble) | K16 steps in this chunk (high nibble)
-  uint8_t commit;  // COMMIT_* after issuing
+struct alignas(16) Chunk {
+  uint8_t layer;     // 0..9 (8 = bottleneck, 9 = direction layer)
+  uint8_t half;      // output columns [128*half, +128)
+  uint8_t src;       // SRC_*: where the A operand of this chunk lives
+  uint8_t a16;       // K offset of the chunk inside that source, in K16 steps
+  uint8_t w16;       // K offset in the layer's padded weight K space (gemm_k), in K16 steps
+  uint8_t steps;     // K16 steps in this chunk
+  uint8_t first;     // first chunk of this (layer, half): accumulate = 0
+  uint8_t wait;      // WAIT_* before the first step
+  uint8_t wait_mid;  // WAIT_* before step `mid` (a chunk that spans two K quarters)
+  uint8_t mid;       // first step of the second part (== steps when there is no second part)
+  uint8_t commit;    // COMMIT_* flags after issuing
+  uint8_t pad;
+  uint16_t off;      // K16 steps of all earlier chunks: byte offset in the image = off * step bytes
+  uint16_t pad2;
 };
 constexpr int kMaxChunks = 160;
 struct ChunkTable {
   Chunk c[kMaxChunks];
   int n_total;       // chunks per tile, full head
   int n_sigma_only;  // chunks per tile through layer 8
+  int steps_total;   // sum of steps
 };
 
+// order inside a layer: half a (enc, hid k 0..255) -> D_a | half b (enc, hid k 0..127) -> A[k0] free |
+// (hid k 128..255) -> D_b
 template <int KC>
 __host__ __device__ constexpr ChunkTable make_chunk_table() {
   ChunkTable t{};
-  int n = 0;
-  constexpr int kHalfChunks = 128 / KC;     // chunks per K half of a hidden layer
-  constexpr int kEncChunks = kXyzPad / KC;  // chunks of the 64-wide xyz embedding
-  constexpr int kStepsFull = KC / 16;
+  int n = 0, off = 0;
   for (int l = 0; l < kNumGemm; ++l) {
     const bool has_enc = (l == 0 || l == 4);
     const bool has_hid = (l != 0);
-    const int enc_chunks = has_enc ? kEncChunks : 0;
-    if (l == 9) {
-      // direction layer: N = 128, one half; A = [bottleneck (TMEM, 256) | dir (smem, 32)]
-      for (int kc = 0; kc < 2 * kHalfChunks; ++kc) {
-        Chunk c{};
-        c.layer = 9; c.half = 0; c.src = SRC_HID; c.kc = kc; c.kpad = kc; c.first = (kc == 0);
-        const int kq = kc * KC;   // K offset; a new quarter starts every 64
-        c.wait = ((kq % 64 == 0) ? (WAIT_A0 + kq / 64) : WAIT_NONE) | (kStepsFull << 4);
-        t.c[n++] = c;
-      }
-      Chunk c{};
-      c.layer = 9; c.src = SRC_DIR; c.kc = 0; c.kpad = 2 * kHalfChunks; c.commit = COMMIT_D0;
-      c.wait = WAIT_DIR | ((kDirPad / 16) << 4);
-      t.c[n++] = c;
-      continue;
-    }
-    // order: half a (enc, hid k0, hid k1) -> D_a | half b (enc, hid k0) -> A[k0] free | (hid k1) -> D_b
-    for (int half = 0; half < 2; ++half) {
+    const int n_halves = l == 9 ? 1 : 2;
+    for (int half = 0; half < n_halves; ++half) {
       bool first = true;
-      for (int kc = 0; kc < enc_chunks; ++kc) {
-        Chunk c{};
-        c.layer = l; c.half = half; c.src = SRC_ENC; c.kc = kc; c.kpad = kc; c.first = first;
-        int w = WAIT_NONE;
-        // layer 1 reads only the embedding; the skip layer's half a overwrites D_a (drained => A0)
-        if (first && half == 0) w = (l == 0) ? WAIT_ENC : WAIT_A0;
-        c.wait = w | (kStepsFull << 4);
-        first = false;
-        if (!has_hid && kc == enc_chunks - 1) c.commit = half == 0 ? COMMIT_D0 : (COMMIT_D1 | COMMIT_AFREE);
-        t.c[n++] = c;
-      }
-      if (has_hid) {
-        for (int kc = 0; kc < 2 * kHalfChunks; ++kc) {
+      // segments of this (layer, half): [enc 64] [hid 256] [dir 32]
+      for (int seg = 0; seg < 3; ++seg) {
+        const int src = seg == 0 ? SRC_ENC : (seg == 1 ? SRC_HID : SRC_DIR);
+        const int klen = seg == 0 ? (has_enc ? kXyzPad : 0) : (seg == 1 ? (has_hid ? kWidth : 0) : (l == 9 ? kDirPad : 0));
+        const int wbase = seg == 0 ? 0 : (seg == 1 ? (has_enc ? kXyzPad : 0) : kWidth);   // padded weight K offset
+        for (int k0 = 0; k0 < klen; k0 += KC) {
+          const int kc = klen - k0 < KC ? klen - k0 : KC;
           Chunk c{};
-          c.layer = l; c.half = half; c.src = SRC_HID; c.kc = kc; c.kpad = enc_chunks + kc; c.first = first;
-          first = false;
-          const int koff = kc * KC;
-          int w = WAIT_NONE;
-          // half a consumes the K quarters as the previous layer's epilogue delivers them; by the
-          // time half b starts, all four are known and D_b is drained (A2/A3 imply it)
-          if (half == 0 && koff % 64 == 0) w = (has_enc && koff == 0) ? WAIT_NONE : WAIT_A0 + koff / 64;
-          c.wait = w | (kStepsFull << 4);
-          if (kc == 2 * kHalfChunks - 1) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
-          if (half == 1 && kc == kHalfChunks - 1) c.commit = COMMIT_AFREE;
+          c.layer = l; c.half = half; c.src = src; c.a16 = k0 / 16; c.w16 = (wbase + k0) / 16; c.steps = kc / 16;
+          c.first = first; c.mid = c.steps; c.off = off;
+          int w = WAIT_NONE, wm = WAIT_NONE;
+          if (src == SRC_ENC && half == 0) w = (l == 0) ? WAIT_ENC : WAIT_A0;   // skip layer: D_a drained
+          if (src == SRC_DIR) w = WAIT_DIR;
+          if (src == SRC_HID && half == 0) {
+            // half a consumes the K quarters as the previous layer's epilogue delivers them
+            if (k0 % 64 == 0) w = (has_enc && k0 == 0) ? WAIT_NONE : WAIT_A0 + k0 / 64;
+            if (kc > 64) { wm = WAIT_A0 + k0 / 64 + 1; c.mid = (64 - k0 % 64) / 16; }
+          }
+          c.wait = w; c.wait_mid = wm;
+          const bool last_of_half = (seg == 2) || (seg == 1 && k0 + kc == klen && l != 9) || (seg == 0 && !has_hid && k0 + kc == klen);
+          if (last_of_half) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
+          // the last reader of A[k 0..127] in this layer: half b's chunk ending at K = 128
+          if (half == 1 && seg == 1 && k0 + kc == 128) c.commit |= COMMIT_AFREE;
+          if (half == 1 && !has_hid && last_of_half) c.commit |= COMMIT_AFREE;
           t.c[n++] = c;
+          off += c.steps;
+          first = false;
         }
       }
     }
     if (l == 7) t.n_sigma_only = n;
   }
   t.n_total = n;
+  t.steps_total = off;
   return t;
 }
-__constant__ ChunkTable c_chunks32 = make_chunk_table<32>();
-__constant__ ChunkTable c_chunks64 = make_chunk_table<64>();
-static constexpr ChunkTable h_chunks32 = make_chunk_table<32>();
-static constexpr ChunkTable h_chunks64 = make_chunk_table<64>();
-static_assert(h_chunks32.n_total == 145 && h_chunks32.n_sigma_only == 120, "chunk schedule (K32)");
-static_assert(h_chunks64.n_total == 73 && h_chunks64.n_sigma_only == 60, "chunk schedule (K64)");
+__constant__ ChunkTable c_chunks_cg1 = make_chunk_table<32>();
+__constant__ ChunkTable c_chunks_cg2 = make_chunk_table<128>();
+static constexpr ChunkTable h_chunks_cg1 = make_chunk_table<32>();
+static constexpr ChunkTable h_chunks_cg2 = make_chunk_table<128>();
+static_assert(h_chunks_cg1.n_total == 145 && h_chunks_cg1.n_sigma_only == 120, "chunk schedule (K32)");
+static_assert(h_chunks_cg2.n_total == 39 && h_chunks_cg2.n_sigma_only == 32, "chunk schedule (K128)");
+static_assert(h_chunks_cg1.steps_total == h_chunks_cg2.steps_total && h_chunks_cg1.steps_total == 290, "K16 steps per tile");
 template <int kCg>
-__device__ __forceinline__ const ChunkTable& chunk_table() { return kCg == 2 ? c_chunks64 : c_chunks32; }
+__device__ __forceinline__ const ChunkTable& chunk_table() { return kCg == 2 ? c_chunks_cg2 : c_chunks_cg1; }
 
-// cta_group used by the tensor-core path (2 unless SNB_TC_CTAGROUP=1); the packed image layout
-// depends on it, so pack and launch read the same value
-static int tc_cta_group() {
-  static const int v = [] {
-    const char* e = getenv("SNB_TC_CTAGROUP");
-    return (e && atoi(e) == 1) ? 1 : 2;
-  }();
-  return v;
-}
+// cta_group used by the tensor-core path.  The kernels stay templated on it (Geo<1> is the
+// single-CTA geometry the CTA-pair design was derived from) but only pairs are instantiated.
+static int tc_cta_group() { return 2; }
 
 // ------------------------------------------------------------------ packed image
 // [PackedHeader 256 B][consts: biases + head weights, fp32][chunk 0][chunk 1]...
@@ -194,14 +179,12 @@ constexpr int kConstFloats = make_const_layout().total;
 constexpr size_t kConstBytes = (size_t)kConstFloats * 4;
 
 __host__ __device__ constexpr bool prec_split(int precision) { return precision != SNB_PREC_BF16; }
-// bytes of one chunk in the image (all CTAs' shares): 128 rows x kKc x 2 B (x2 with the lo part)
-__host__ __device__ constexpr uint32_t chunk_bytes(int precision, int kc) {
-  return (uint32_t)(kNh * kc * 2 * (prec_split(precision) ? 2 : 1));
+// image bytes of one K16 step of a chunk (all CTAs' shares, hi and lo): 128 rows x 16 K x 2 B (x2)
+__host__ __device__ constexpr uint32_t step_image_bytes(int precision) {
+  return (uint32_t)(kNh * 16 * 2 * (prec_split(precision) ? 2 : 1));
 }
 size_t tc_packed_bytes(int precision) {
-  const bool cg2 = tc_cta_group() == 2;
-  return sizeof(PackedHeader) + kConstBytes +
-         (size_t)(cg2 ? h_chunks64.n_total : h_chunks32.n_total) * chunk_bytes(precision, cg2 ? 64 : 32);
+  return sizeof(PackedHeader) + kConstBytes + (size_t)h_chunks_cg2.steps_total * step_image_bytes(precision);
 }
 
 // 16-bit conversions -------------------------------------------------------------------
@@ -293,28 +276,32 @@ __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation
     else if (e >= CL.rgb_b && e < CL.rgb_b + 3) v = pp.p[kRgbB][e - CL.rgb_b];
     cst[e] = v;
   }
-  // chunk image: [CTA 0 share: hi | lo][CTA 1 share: hi | lo]; a share is the canonical
-  // (SWIZZLE_NONE, K-major) block [k8][kRowsB rows][8 elements]
-  constexpr uint32_t kShare = G::kPartBytes * (kSplit ? 2 : 1);
-  constexpr int per_chunk = kNh * G::kKc;
-  for (int e = gtid; e < tab.n_total * per_chunk; e += gsz) {
-    const int ci = e / per_chunk, rem = e - ci * per_chunk;
-    const int r = rem / G::kKc, kk = rem - r * G::kKc;
+  // chunk image: [CTA 0 share: hi | lo][CTA 1 share: hi | lo]; each of hi / lo is the canonical
+  // (SWIZZLE_NONE, K-major) block [k8][kRowsB rows][8 elements] of the chunk's 16*steps K columns
+  constexpr int kParts = kSplit ? 2 : 1;
+  const int total = tab.steps_total * kNh * 16;
+  for (int e = gtid; e < total; e += gsz) {
+    const int gstep = e / (kNh * 16), rem = e - gstep * (kNh * 16);
+    const int r = rem >> 4, k16 = rem & 15;
+    int ci = 0;
+    while (ci + 1 < tab.n_total && gstep >= tab.c[ci + 1].off) ++ci;
     const Chunk c = tab.c[ci];
+    const int kk = (gstep - c.off) * 16 + k16;       // K index inside the chunk
     const int l = c.layer;
     const int n = c.half * kNh + r;
-    const int kpad = c.kpad * G::kKc + kk;
+    const int kpad = c.w16 * 16 + kk;
     const int col = kpad < gemm_k(l) ? gemm_src_col(l, kpad) : -1;
     const int src_k = l == 0 ? 63 : (l == 4 ? 319 : (l == 9 ? 283 : 256));
     const float w = col >= 0 ? pp.p[param_weight_index(l)][n * src_k + col] : 0.f;
     const int owner = r / G::kRowsB, rr = r - owner * G::kRowsB;
-    unsigned char* base = chunks + (size_t)ci * (kShare * kCg) + (size_t)owner * kShare;
+    const uint32_t part = G::kStepBytes * c.steps;                // bytes of one of {hi, lo} of a share
+    unsigned char* base = chunks + (size_t)c.off * (G::kStepBytes * kParts * kCg) + (size_t)owner * part * kParts;
     const uint32_t off = (uint32_t)(kk >> 3) * (G::kRowsB * 16) + rr * 16 + (kk & 7) * 2;
     if (kSplit) {
       uint16_t hi, lo;
       split16<kBf16>(w, hi, lo);
       *reinterpret_cast<uint16_t*>(base + off) = hi;
-      *reinterpret_cast<uint16_t*>(base + G::kPartBytes + off) = lo;
+      *reinterpret_cast<uint16_t*>(base + part + off) = lo;
     } else {
       *reinterpret_cast<uint16_t*>(base + off) = cvt16<kBf16>(w);
     }
@@ -335,21 +322,22 @@ int launch_pack_tc(const float* const* params, int precision, int new_activation
   ParamPtrsTc pp;
   for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i) pp.p[i] = params[i];
   unsigned char* img = reinterpret_cast<unsigned char*>(image);
-  return tc_cta_group() == 2 ? launch_pack_tc_cg<2>(pp, precision, new_activation, img, st)
-                             : launch_pack_tc_cg<1>(pp, precision, new_activation, img, st);
+  return launch_pack_tc_cg<2>(pp, precision, new_activation, img, st);
 }
 
 // ------------------------------------------------------------------ shared memory
 template <bool kSplit, int kCg>
 struct TcSmem {
-  static constexpr uint32_t kStageBytes = Geo<kCg>::kPartBytes * (kSplit ? 2 : 1);   // this CTA's share of a chunk
   static constexpr int kParts = kSplit ? 2 : 1;
+  static constexpr uint32_t kStageBytes = Geo<kCg>::kPartBytesMax * kParts;   // this CTA's share of a full chunk
+  static constexpr int kStagesRaw = (160 * 1024) / kStageBytes;              // up to 160 KB of weights in flight
+  static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
   alignas(1024) unsigned char ring[kStages][kStageBytes];
   alignas(128) unsigned char enc[kParts][kTile * kXyzPad * 2];   // canonical [k8][row][8] hi (, lo)
   alignas(128) unsigned char dir[kParts][kTile * kDirPad * 2];
   alignas(16) float cst[kConstFloats];
   float part[2][4][kTile];        // head partial sums [column half][sigma,r,g,b][row]
-  uint64_t full[kStages], empty[kStages];
+  uint64_t full[16], empty[16];
   uint64_t d_full[2], a_ready[4], a_free, enc_ready, dir_ready, d_drained;
   uint32_t tmem_base;
 };
@@ -385,6 +373,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   constexpr ConstLayout CL = make_const_layout();
   constexpr uint32_t kStageBytes = Smem::kStageBytes;
+  constexpr int kStages = Smem::kStages;
+  constexpr int kParts = Smem::kParts;
+  static_assert(kStages <= 16, "barrier arrays");
   const ChunkTable& tab = chunk_table<kCg>();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(p.image);
@@ -430,8 +421,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
         for (int ci = 0; ci < n_chunks; ++ci, ++it) {
           const uint32_t st = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(&s.empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&s.full[st], kStageBytes);
-          bulk_g2s(s.ring[st], g_chunks + ((size_t)ci * kCg + cta_rank) * kStageBytes, kStageBytes, &s.full[st]);
+          const Chunk c = tab.c[ci];
+          const uint32_t share = G::kStepBytes * kParts * c.steps;      // this CTA's bytes of the chunk
+          const unsigned char* src = g_chunks + (size_t)c.off * (G::kStepBytes * kParts * kCg) + (size_t)cta_rank * share;
+          mbar_arrive_expect_tx(&s.full[st], share);
+          for (uint32_t o = 0; o < share; o += 16384)
+            bulk_g2s(s.ring[st] + o, src + o, share - o < 16384 ? share - o : 16384, &s.full[st]);
         }
       }
     }
@@ -475,49 +470,86 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       for (int ci = 0; ci < n_chunks; ++ci, ++it) {
         const Chunk c = c_next;
         c_next = tab.c[ci + 1 < n_chunks ? ci + 1 : 0];   // prefetch the next entry (constant-cache latency)
-        const int w = c.wait & 15, steps = c.wait >> 4;
         const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3 && lane == 0;
         trace(tr, ci * 4 + 0);
-        if (w == WAIT_ENC) { wait_bar(&s.enc_ready, ph_enc); ph_enc ^= 1; }
-        else if (w == WAIT_DIR) { wait_bar(&s.dir_ready, ph_dir); ph_dir ^= 1; }
-        else if (w >= WAIT_A0) { const int q = w - WAIT_A0; wait_bar(&s.a_ready[q], (ph_a >> q) & 1); ph_a ^= 1u << q; }
+        auto wait_code = [&](int w) {
+          if (w == WAIT_ENC) { wait_bar(&s.enc_ready, ph_enc); ph_enc ^= 1; }
+          else if (w == WAIT_DIR) { wait_bar(&s.dir_ready, ph_dir); ph_dir ^= 1; }
+          else if (w >= WAIT_A0) { const int q = w - WAIT_A0; wait_bar(&s.a_ready[q], (ph_a >> q) & 1); ph_a ^= 1u << q; }
+        };
+        wait_code(c.wait);
         const uint32_t st = it % kStages, ph = (it / kStages) & 1;
         trace(tr, ci * 4 + 1);
         wait_bar(&s.full[st], ph);
         tc_fence_after();
         trace(tr, ci * 4 + 2);
-        if (elect_one()) {
-          if (!(p.debug & 4)) {
-            const uint32_t d = tbase + kColD + (c.layer == 9 ? 0 : c.half * kNh);
-            const uint64_t b_hi = desc_b0 + ((ring0 + st * kStageBytes) >> 4);
-            const uint64_t b_lo = b_hi + (G::kPartBytes >> 4);
-            if (c.src == SRC_HID) {
-              const uint32_t a_hi = tbase + kColAhi + ((uint32_t)(c.kc * G::kKc) >> 1);
-              const uint32_t a_lo = tbase + kColAlo + ((uint32_t)(c.kc * G::kKc) >> 1);
+        const uint32_t d = tbase + kColD + (c.layer == 9 ? 0 : c.half * kNh);
+        // descriptors as (lo, hi) words: only the start-address field in the low word moves
+        const uint32_t bd_hi32 = (uint32_t)(desc_b0 >> 32), ad_hi32 = (uint32_t)(desc_a0 >> 32);
+        const uint32_t bh = (uint32_t)desc_b0 + ((ring0 + st * kStageBytes) >> 4);       // W_hi block
+        const uint32_t bl = bh + ((G::kStepBytes * c.steps) >> 4);                         // W_lo block
+        // K16 steps [kLo, kHi) of this chunk, fully unrolled (compile-time ranges: no per-step predicates)
+        auto issue_range = [&](auto lo_tag, auto hi_tag) {
+          constexpr int kLo = decltype(lo_tag)::value, kHi = decltype(hi_tag)::value;
+          if (c.src == SRC_HID) {
+            const uint32_t a_hi = tbase + kColAhi + (uint32_t)c.a16 * 8;
+            const uint32_t a_lo = tbase + kColAlo + (uint32_t)c.a16 * 8;
 #pragma unroll
-              for (int ks = 0; ks < G::kSteps; ++ks) {
-                issue_ts(d, a_hi + ks * 8, b_hi + ks * kStepB, (c.first && ks == 0) ? 0u : 1u);
+            for (int ks = kLo; ks < kHi; ++ks) {
+              const uint32_t acc = (ks == 0 && c.first) ? 0u : 1u;
+              if (kCg == 2) {
+                mma2_ts_lohi(d, a_hi + ks * 8, bh + ks * kStepB, bd_hi32, idesc, acc);
                 if (kSplit) {
-                  issue_ts(d, a_lo + ks * 8, b_hi + ks * kStepB, 1);
-                  issue_ts(d, a_hi + ks * 8, b_lo + ks * kStepB, 1);
+                  mma2_ts_lohi(d, a_lo + ks * 8, bh + ks * kStepB, bd_hi32, idesc, 1);
+                  mma2_ts_lohi(d, a_hi + ks * 8, bl + ks * kStepB, bd_hi32, idesc, 1);
                 }
+              } else {
+                const uint64_t b1 = ((uint64_t)bd_hi32 << 32) | (bh + ks * kStepB), b2 = ((uint64_t)bd_hi32 << 32) | (bl + ks * kStepB);
+                mma_ts(d, a_hi + ks * 8, b1, idesc, acc);
+                if (kSplit) { mma_ts(d, a_lo + ks * 8, b1, idesc, 1); mma_ts(d, a_hi + ks * 8, b2, idesc, 1); }
               }
-            } else {
-              const uint32_t a_off = (uint32_t)(c.kc * (G::kKc / 8)) * (kTile * 16);
-              const uint64_t a_hi = desc_a0 + (((c.src == SRC_ENC ? enc_hi : dir_hi) + a_off) >> 4);
-              const uint64_t a_lo = desc_a0 + (((c.src == SRC_ENC ? enc_lo : dir_lo) + a_off) >> 4);
+            }
+          } else {
+            const uint32_t a_off = (uint32_t)c.a16 * 2 * (kTile * 16);
+            const uint32_t ah = (uint32_t)desc_a0 + (((c.src == SRC_ENC ? enc_hi : dir_hi) + a_off) >> 4);
+            const uint32_t al = (uint32_t)desc_a0 + (((c.src == SRC_ENC ? enc_lo : dir_lo) + a_off) >> 4);
 #pragma unroll
-              for (int ks = 0; ks < G::kSteps; ++ks) {
-                if (ks < steps) {
-                  issue_ss(d, a_hi + ks * kStepA, b_hi + ks * kStepB, (c.first && ks == 0) ? 0u : 1u);
-                  if (kSplit) {
-                    issue_ss(d, a_lo + ks * kStepA, b_hi + ks * kStepB, 1);
-                    issue_ss(d, a_hi + ks * kStepA, b_lo + ks * kStepB, 1);
-                  }
+            for (int ks = kLo; ks < kHi; ++ks) {
+              const uint32_t acc = (ks == 0 && c.first) ? 0u : 1u;
+              if (kCg == 2) {
+                mma2_ss_lohi(d, ah + ks * kStepA, ad_hi32, bh + ks * kStepB, bd_hi32, idesc, acc);
+                if (kSplit) {
+                  mma2_ss_lohi(d, al + ks * kStepA, ad_hi32, bh + ks * kStepB, bd_hi32, idesc, 1);
+                  mma2_ss_lohi(d, ah + ks * kStepA, ad_hi32, bl + ks * kStepB, bd_hi32, idesc, 1);
                 }
+              } else {
+                const uint64_t a1 = ((uint64_t)ad_hi32 << 32) | (ah + ks * kStepA), a2 = ((uint64_t)ad_hi32 << 32) | (al + ks * kStepA);
+                const uint64_t b1 = ((uint64_t)bd_hi32 << 32) | (bh + ks * kStepB), b2 = ((uint64_t)bd_hi32 << 32) | (bl + ks * kStepB);
+                mma_ss(d, a1, b1, idesc, acc);
+                if (kSplit) { mma_ss(d, a2, b1, idesc, 1); mma_ss(d, a1, b2, idesc, 1); }
               }
             }
           }
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using IH = std::integral_constant<int, G::kMaxSteps / 2>;
+        using IF = std::integral_constant<int, G::kMaxSteps>;
+        using I2 = std::integral_constant<int, 2>;
+        const bool do_mma = !(p.debug & 4);
+        const bool two_part = c.mid < c.steps;          // only full chunks are split (at the K-quarter boundary)
+        if (elect_one() && do_mma) {
+          if (c.steps == G::kMaxSteps) { if (two_part) issue_range(I0{}, IH{}); else issue_range(I0{}, IF{}); }
+          else if (c.steps == G::kMaxSteps / 2) issue_range(I0{}, IH{});
+          else issue_range(I0{}, I2{});
+        }
+        __syncwarp();
+        if (two_part) {
+          wait_code(c.wait_mid);
+          tc_fence_after();
+          if (elect_one() && do_mma) issue_range(IH{}, IF{});
+          __syncwarp();
+        }
+        if (elect_one()) {
           commit(&s.empty[st]);        // ring slot free (in both CTAs of a pair) once these MMAs retire
           if (c.commit & COMMIT_AFREE) commit(&s.a_free);
           if (c.commit & COMMIT_D0) commit(&s.d_full[0]);
@@ -546,50 +578,63 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     // ---- positional encodings of one tile -> smem (canonical, hi/lo).  Split in pieces so they
     // fit the epilogue warps' idle windows: xyz part 0 (identity + 3 of this thread's 5
     // frequencies), xyz part 1 (the other 2 + zero pad), and the direction embedding.
-    auto put_enc = [&](int k, float v) {
-      uint16_t hi, lo;
-      if (kSplit) split16<kBf16>(v, hi, lo); else { hi = cvt16<kBf16>(v); lo = 0; }
-      *reinterpret_cast<uint16_t*>(s.enc[0] + canon_off(row, k)) = hi;
-      if (kSplit) *reinterpret_cast<uint16_t*>(s.enc[kSplit ? 1 : 0] + canon_off(row, k)) = lo;
-    };
-    auto put_dir = [&](int k, float v) {
-      uint16_t hi, lo;
-      if (kSplit) split16<kBf16>(v, hi, lo); else { hi = cvt16<kBf16>(v); lo = 0; }
-      *reinterpret_cast<uint16_t*>(s.dir[0] + canon_off(row, k)) = hi;
-      if (kSplit) *reinterpret_cast<uint16_t*>(s.dir[kSplit ? 1 : 0] + canon_off(row, k)) = lo;
+    // 8 consecutive channels (one 16-byte core-matrix row) -> hi (and lo) vector stores
+    auto put8 = [&](unsigned char* hi_base, unsigned char* lo_base, int k8, const float (&v)[8]) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_pair<kBf16, kSplit>(v[2 * j], v[2 * j + 1], h[j], l[j]);
+      const uint32_t off = (uint32_t)k8 * (kTile * 16) + row * 16;
+      *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      if (kSplit) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
     };
     auto tile_of = [&](long long slot) { return (group + slot * n_groups) * kCg + cta_rank; };
+    // 16 consecutive channels [c_lo, c_lo+16) of Embedding(3, L)(x): [x(3), sin(2^0 x)(3), cos(2^0 x)(3),
+    // sin(2^1 x)(3), ...] (nerf.py:36-41), one sincosf per (frequency, coordinate) that the window touches
+    auto embed16 = [&](const float (&x)[3], int c_lo, int n_ch, int n_freqs, float (&v)[16]) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (c_lo + j < 3) ? x[(c_lo + j) % 3] : 0.f;   // identity / zero pad
+      for (int f = 0; f < n_freqs; ++f) {
+        const int base = 3 + 6 * f;
+        if (base + 6 <= c_lo || base >= c_lo + 16) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int js = base + c - c_lo, jc = js + 3;
+          if ((js >= 0 && js < 16) || (jc >= 0 && jc < 16)) {
+            float sn, cs;
+            sincosf(x[c] * (float)(1 << f), &sn, &cs);
+            if (js >= 0 && js < 16) v[js] = sn;
+            if (jc >= 0 && jc < 16 && base + 3 + c < n_ch) v[jc] = cs;
+          }
+        }
+      }
+    };
+    // xyz embedding of one tile: this thread writes 32 of the 64 channels of its row (two parts of 16,
+    // so the work can be spread over two idle windows)
     auto encode_xyz = [&](long long slot, int part) {
       const long long pt = tile_of(slot) * kTile + row;
+      const int c_lo = (ch * 4 + part * 2) * 8;
+      float v[16];
       if (kEmbedded) {
         const float* xr = p.x + pt * p.x_stride;
-        for (int k = ch * 32 + part * 16; k < ch * 32 + part * 16 + 16; ++k)
-          put_enc(k, (pt < p.n_points && k < kXyzCh) ? xr[k] : 0.f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (pt < p.n_points && c_lo + j < kXyzCh) ? xr[c_lo + j] : 0.f;
       } else {
-        float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, zz = 0.f;
+        float x[3] = {0.f, 0.f, 0.f};
         if (pt < p.n_points) {
           const long long ray = pt / p.n_samples;
           const float4 r0 = *reinterpret_cast<const float4*>(p.rays + ray * 8);
           const float4 r1 = *reinterpret_cast<const float4*>(p.rays + ray * 8 + 4);
-          o[0] = r0.x; o[1] = r0.y; o[2] = r0.z;
-          d[0] = r0.w; d[1] = r1.x; d[2] = r1.y;
-          zz = p.z[pt];
+          const float zz = p.z[pt];
+          x[0] = __fadd_rn(r0.x, __fmul_rn(r0.w, zz));   // rendering.py:284-285 rounding
+          x[1] = __fadd_rn(r0.y, __fmul_rn(r1.x, zz));
+          x[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, zz));
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float x = __fadd_rn(o[c], __fmul_rn(d[c], zz));   // rendering.py:284-285 rounding
-          if (part == 0 && ch == 0) put_enc(c, x);
-          const int f0 = part == 0 ? 0 : 3, f1 = part == 0 ? 3 : 5;
-          for (int f = f0; f < f1; ++f) {
-            const int fr = ch * 5 + f;
-            float sn, cs;
-            sincosf(x * (float)(1 << fr), &sn, &cs);
-            put_enc(3 + fr * 6 + c, sn);
-            put_enc(3 + fr * 6 + 3 + c, cs);
-          }
-        }
-        if (part == 1 && ch == 1) put_enc(kXyzCh, 0.f);
+        embed16(x, c_lo, kXyzCh, SNB_XYZ_FREQS, v);
       }
+      const float va[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+      const float vb[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+      put8(s.enc[0], s.enc[kSplit ? 1 : 0], c_lo / 8, va);
+      put8(s.enc[0], s.enc[kSplit ? 1 : 0], c_lo / 8 + 1, vb);
       if (part == 1) {
         fence_proxy_async_smem();     // generic-proxy smem writes -> visible to tcgen05.mma
         signal(&s.enc_ready);
@@ -597,34 +642,26 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     };
     auto encode_dir = [&](long long slot) {
       const long long pt = tile_of(slot) * kTile + row;
+      const int c_lo = ch * 16;
+      float v[16];
       if (kEmbedded) {
         const int nin = p.sigma_only ? kXyzCh : kXyzCh + kDirCh;
         const float* xr = p.x + pt * p.x_stride;
-        for (int k = ch * 16; k < ch * 16 + 16; ++k)
-          put_dir(k, (pt < p.n_points && k < kDirCh && kXyzCh + k < nin) ? xr[kXyzCh + k] : 0.f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          v[j] = (pt < p.n_points && c_lo + j < kDirCh && kXyzCh + c_lo + j < nin) ? xr[kXyzCh + c_lo + j] : 0.f;
       } else {
         float d[3] = {0.f, 0.f, 0.f};
         if (pt < p.n_points) {
           const long long ray = pt / p.n_samples;
           d[0] = p.rays[ray * 8 + 3]; d[1] = p.rays[ray * 8 + 4]; d[2] = p.rays[ray * 8 + 5];
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (ch == 0) put_dir(c, d[c]);
-#pragma unroll
-          for (int f = 0; f < 2; ++f) {
-            const int fr = ch * 2 + f;
-            float sn, cs;
-            sincosf(d[c] * (float)(1 << fr), &sn, &cs);
-            put_dir(3 + fr * 6 + c, sn);
-            put_dir(3 + fr * 6 + 3 + c, cs);
-          }
-        }
-        if (ch == 1) {
-#pragma unroll
-          for (int k = kDirCh; k < kDirPad; ++k) put_dir(k, 0.f);
-        }
+        embed16(d, c_lo, kDirCh, SNB_DIR_FREQS, v);
       }
+      const float va[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+      const float vb[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+      put8(s.dir[0], s.dir[kSplit ? 1 : 0], c_lo / 8, va);
+      put8(s.dir[0], s.dir[kSplit ? 1 : 0], c_lo / 8 + 1, vb);
       fence_proxy_async_smem();
       signal(&s.dir_ready);
     };
@@ -832,7 +869,7 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
 
 template <bool kBf16, bool kSplit, bool kEmbedded>
 static int launch_tc_cg(const TcParams& p, cudaStream_t st) {
-  return tc_cta_group() == 2 ? launch_tc<kBf16, kSplit, kEmbedded, 2>(p, st) : launch_tc<kBf16, kSplit, kEmbedded, 1>(p, st);
+  return launch_tc<kBf16, kSplit, kEmbedded, 2>(p, st);
 }
 
 template <bool kEmbedded>

@@ -226,6 +226,27 @@ __device__ __forceinline__ void mma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Variants that take the smem descriptors as (lo, hi) 32-bit halves: between the MMAs of a chunk
+// only the 14-bit start-address field (low word) changes, so the issuing thread does 32-bit adds.
+__device__ __forceinline__ void mma2_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo32, uint32_t b_hi32,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo32), "r"(b_hi32), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void mma2_ss_lohi(uint32_t d_tmem, uint32_t a_lo32, uint32_t a_hi32, uint32_t b_lo32,
+                                             uint32_t b_hi32, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 ad, {%1, %2};\n\t"
+      "mov.b64 bd, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo32), "r"(a_hi32), "r"(b_lo32), "r"(b_hi32), "r"(idesc), "r"(accumulate));
+}
 // completion of all prior MMAs arrives on the barrier at this smem offset in both CTAs of the pair
 __device__ __forceinline__ void mma2_commit(uint64_t* bar) {
   asm volatile(
