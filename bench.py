@@ -329,7 +329,10 @@ def main():
         value = n * world / (ms_per_step / 1e3)
         e2e_value = n * world / ((e2e_ms / args.steps) / 1e3)
         kern_tflops = FLOP_PER_POINT * n * S_f / (kern_ms / 1e3) / 1e12
-        tensor_peak = peaks.get("bf16_tflops_sustained" if kern_ms > 50 else "bf16_tflops")
+        # the kernel is timed alone but in a back-to-back loop of tens of ms each: the power-capped
+        # ("sustained") cuBLAS figure is the comparable denominator
+        tensor_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+        passes = 3 if precision.endswith("x3") else 1
         traffic = None
         tp = os.path.join(ROOT, "profiles", "field_traffic.json")
         if os.path.exists(tp):
@@ -353,7 +356,9 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "fine-pass field kernel (160000 rays x 128 samples)",
                          "achieved": kern_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": kern_tflops / tensor_peak if tensor_peak else None, "traffic": traffic,
-                         "peak_source": f"MEASURED_PEAKS.json ({peaks['_source']}), dense bf16 cuBLAS",
+                         "executed_tflops": kern_tflops * passes if precision != "fp32" else None,
+                         "frac_executed": kern_tflops * passes / tensor_peak if (tensor_peak and precision != "fp32") else None,
+                         "peak_source": f"MEASURED_PEAKS.json ({peaks['_source']}), dense bf16 cuBLAS, sustained",
                          "ms_per_launch": kern_ms,
                          "flops": "algorithmic 2*593408 per point (SURVEY 8d); "
                                   + ("executed MMA flops are 3x (hi*hi + hi*lo + lo*hi)" if precision.endswith("x3")
