@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-echo "=== bench (auto precision)"; timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; tail -c 2600 gpurun_out/bench_r01.json; tail -3 gpurun_out/bench_r01.err
-echo "=== bench bf16"; timeout 300 python bench.py --steps 5 --warmup 3 --precision bf16 --no-cpu-baseline > gpurun_out/bench_r01_bf16.json 2> gpurun_out/bench_r01_bf16.err; tail -c 900 gpurun_out/bench_r01_bf16.json | head -c 700
-echo; echo "=== reference arm"; timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r01_reference.json 2> gpurun_out/bench_r01_reference.err; tail -c 700 gpurun_out/bench_r01_reference.json
-echo "=== ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_f16x3.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -1 gpurun_out/ncu_bench.log | head -c 300
-echo "=== ncu full field_tc (full size)"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:field_tc -s 2 -c 1 -o gpurun_out/prof_tc_final python tools/time_field.py --precision f16x3 --iters 1 > gpurun_out/ncu_tc.log 2>&1; tail -2 gpurun_out/ncu_tc.log
+nvidia-smi -L | head -3
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_r01_2gpu.json 2> gpurun_out/bench_r01_2gpu.err; tail -c 1500 gpurun_out/bench_r01_2gpu.json; tail -5 gpurun_out/bench_r01_2gpu.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_r01_2gpu_ref.json 2> gpurun_out/bench_r01_2gpu_ref.err; tail -c 300 gpurun_out/bench_r01_2gpu_ref.json

@@ -103,6 +103,7 @@ def test_mlp_forward_matches_golden(tag, params):
     m.load_state_dict(p)
     m = m.to(DEV)
     x = t(ST["mlp_in"]).to(DEV)
+    before = sinnerf_b200.get_precision()
     for mode in available_modes():
         sinnerf_b200.set_precision(mode)
         try:
@@ -115,7 +116,7 @@ def test_mlp_forward_matches_golden(tag, params):
                 s = m(x[:, :63].contiguous(), sigma_only=True).cpu()
                 assert_close(s, ST["mlp_seed0_sigma"], tol, f"{mode}:sigma_only")
         finally:
-            sinnerf_b200.set_precision("fp32")
+            sinnerf_b200.set_precision(before)
 
 
 def test_mlp_old_activation():
@@ -125,8 +126,16 @@ def test_mlp_old_activation():
     p = {k: v.clone() for k, v in m.state_dict().items()}
     x = t(ST["mlp_in"])
     ref = orc.field_mlp(p, x[:, :63], x[:, 63:], new_activation=False)
-    out = m.to(DEV)(x.to(DEV)).cpu()
-    assert_close(out, ref, 1e-4, "relu/sigmoid variant")
+    m = m.to(DEV)
+    import sinnerf_b200
+    before = sinnerf_b200.get_precision()
+    try:
+        for mode in fp32_class_modes():
+            sinnerf_b200.set_precision(mode)
+            out = m(x.to(DEV)).cpu()
+            assert_close(out, ref, 1e-4, f"relu/sigmoid variant ({mode})")
+    finally:
+        sinnerf_b200.set_precision(before)
 
 
 def test_sample_pdf_known_answers_and_golden():
