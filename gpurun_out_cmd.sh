@@ -1,4 +1,7 @@
 mkdir -p gpurun_out
-nvidia-smi -L | head -3
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_r01_2gpu.json 2> gpurun_out/bench_r01_2gpu.err; tail -c 1500 gpurun_out/bench_r01_2gpu.json; tail -5 gpurun_out/bench_r01_2gpu.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_r01_2gpu_ref.json 2> gpurun_out/bench_r01_2gpu_ref.err; tail -c 300 gpurun_out/bench_r01_2gpu_ref.json
+echo "=== pytest all gpu"; timeout 600 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; grep -E "AssertionError|passed|failed|^FAILED|rc=" gpurun_out/pytest_gpu.log | head -12
+echo "=== timing"
+for p in f16x3 bf16x3 bf16; do timeout 120 python tools/time_field.py --precision $p --iters 3 2>&1 | tail -1; done | tee gpurun_out/timing_cg2.log
+timeout 120 python tools/time_field.py --precision f16x3 --iters 3 --samples 64 2>&1 | tail -1 | tee -a gpurun_out/timing_cg2.log
+echo "=== bench"; timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; head -c 420 gpurun_out/bench_r01.json; echo; tail -c 900 gpurun_out/bench_r01.json; tail -3 gpurun_out/bench_r01.err
+echo "=== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -4

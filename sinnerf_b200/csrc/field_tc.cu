@@ -24,7 +24,10 @@
 //   * positional encodings (63->64, 27->32 columns) are computed by the epilogue warps into
 //     shared memory in the canonical layout and consumed by ".ss" MMAs at layers 1, 5 (skip)
 //     and the direction layer, so neither concat exists;
-//   * sigma (256->1) and rgb (128->3) heads are fp32 dot products inside the epilogue.
+//   * sigma (256->1) and rgb (128->3) heads are fp32 dot products inside the epilogue;
+//   * the bottleneck layer (256->256, no activation, nerf.py:140) is folded into the direction layer at
+//     pack time: Wd[:, :256] (Wf h + bf) = (Wd[:, :256] Wf) h + Wd[:, :256] bf -- one 256-wide layer
+//     (11 % of the MMA work) less per point, same function up to fp32 rounding.
 //
 // Schedule inside a layer (N = 256 split in halves a|b, K = 256 in halves 0|1):
 //     (a,k0) (a,k1) -> D_a full | (b,k0) -> A[k0] free | (b,k1) -> D_b full
@@ -103,6 +106,7 @@ __host__ __device__ constexpr ChunkTable make_chunk_table() {
   ChunkTable t{};
   int n = 0, off = 0;
   for (int l = 0; l < kNumGemm; ++l) {
+    if (l == 8) continue;   // bottleneck: folded into the direction layer's weights (pack_tc_kernel)
     const bool has_enc = (l == 0 || l == 4);
     const bool has_hid = (l != 0);
     const int n_halves = l == 9 ? 1 : 2;
@@ -148,9 +152,9 @@ __constant__ ChunkTable c_chunks_cg1 = make_chunk_table<32>();
 __constant__ ChunkTable c_chunks_cg2 = make_chunk_table<128>();
 static constexpr ChunkTable h_chunks_cg1 = make_chunk_table<32>();
 static constexpr ChunkTable h_chunks_cg2 = make_chunk_table<128>();
-static_assert(h_chunks_cg1.n_total == 145 && h_chunks_cg1.n_sigma_only == 120, "chunk schedule (K32)");
-static_assert(h_chunks_cg2.n_total == 39 && h_chunks_cg2.n_sigma_only == 32, "chunk schedule (K128)");
-static_assert(h_chunks_cg1.steps_total == h_chunks_cg2.steps_total && h_chunks_cg1.steps_total == 290, "K16 steps per tile");
+static_assert(h_chunks_cg1.n_total == 129 && h_chunks_cg1.n_sigma_only == 120, "chunk schedule (K32)");
+static_assert(h_chunks_cg2.n_total == 35 && h_chunks_cg2.n_sigma_only == 32, "chunk schedule (K128)");
+static_assert(h_chunks_cg1.steps_total == h_chunks_cg2.steps_total && h_chunks_cg1.steps_total == 258, "K16 steps per tile");
 template <int kCg>
 __device__ __forceinline__ const ChunkTable& chunk_table() { return kCg == 2 ? c_chunks_cg2 : c_chunks_cg1; }
 
@@ -183,8 +187,13 @@ __host__ __device__ constexpr bool prec_split(int precision) { return precision 
 __host__ __device__ constexpr uint32_t step_image_bytes(int precision) {
   return (uint32_t)(kNh * 16 * 2 * (prec_split(precision) ? 2 : 1));
 }
+// scratch at the end of the image: W' = Wd[:, :256] Wf (128 x 256) and b' = bd + Wd[:, :256] bf (128)
+constexpr size_t kFusedFloats = (size_t)kHalf * kWidth + kHalf;
+__host__ __device__ constexpr size_t chunks_bytes(int precision) {
+  return (size_t)make_chunk_table<128>().steps_total * step_image_bytes(precision);
+}
 size_t tc_packed_bytes(int precision) {
-  return sizeof(PackedHeader) + kConstBytes + (size_t)h_chunks_cg2.steps_total * step_image_bytes(precision);
+  return sizeof(PackedHeader) + kConstBytes + chunks_bytes(precision) + kFusedFloats * sizeof(float);
 }
 
 // 16-bit conversions -------------------------------------------------------------------
@@ -249,6 +258,21 @@ struct ParamPtrsTc {
   const float* p[SNB_N_PARAM_TENSORS];
 };
 
+// W'[n][k] = sum_j Wd[n][j] Wf[j][k],  b'[n] = bd[n] + sum_j Wd[n][j] bf[j]   (double accumulation)
+__global__ void fuse_bottleneck_kernel(ParamPtrsTc pp, float* fused) {
+  const float* Wd = pp.p[18];   // (128, 283)
+  const float* Wf = pp.p[16];   // (256, 256)
+  const float* bf = pp.p[17];
+  const float* bd = pp.p[19];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kHalf * (kWidth + 1); e += gridDim.x * blockDim.x) {
+    const int n = e / (kWidth + 1), k = e - n * (kWidth + 1);
+    double acc = k == kWidth ? (double)bd[n] : 0.0;
+    for (int j = 0; j < kWidth; ++j) acc += (double)Wd[n * 283 + j] * (double)(k == kWidth ? bf[j] : Wf[j * kWidth + k]);
+    if (k == kWidth) fused[kHalf * kWidth + n] = (float)acc;
+    else fused[n * kWidth + k] = (float)acc;
+  }
+}
+
 template <bool kBf16, bool kSplit, int kCg>
 __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation, unsigned char* image) {
   using G = Geo<kCg>;
@@ -257,6 +281,7 @@ __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation
   PackedHeader* hdr = reinterpret_cast<PackedHeader*>(image);
   float* cst = reinterpret_cast<float*>(image + sizeof(PackedHeader));
   unsigned char* chunks = image + sizeof(PackedHeader) + kConstBytes;
+  const float* fused = reinterpret_cast<const float*>(chunks + chunks_bytes(precision));   // fuse_bottleneck_kernel
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
   if (gtid == 0) {
     hdr->magic = kMagic;
@@ -269,7 +294,7 @@ __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation
     if (e < CL.sigma_w) {
       int l = 0;
       while (l + 1 < kNumGemm && e >= CL.b[l + 1]) ++l;
-      v = pp.p[param_weight_index(l) + 1][e - CL.b[l]];
+      v = l == 9 ? fused[kHalf * kWidth + (e - CL.b[l])] : pp.p[param_weight_index(l) + 1][e - CL.b[l]];
     } else if (e < CL.sigma_b) v = pp.p[kSigmaW][e - CL.sigma_w];
     else if (e == CL.sigma_b) v = pp.p[kSigmaB][0];
     else if (e >= CL.rgb_w && e < CL.rgb_b) v = pp.p[kRgbW][e - CL.rgb_w];
@@ -292,7 +317,8 @@ __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation
     const int kpad = c.w16 * 16 + kk;
     const int col = kpad < gemm_k(l) ? gemm_src_col(l, kpad) : -1;
     const int src_k = l == 0 ? 63 : (l == 4 ? 319 : (l == 9 ? 283 : 256));
-    const float w = col >= 0 ? pp.p[param_weight_index(l)][n * src_k + col] : 0.f;
+    float w = col >= 0 ? pp.p[param_weight_index(l)][n * src_k + col] : 0.f;
+    if (l == 9 && kpad < kWidth) w = fused[n * kWidth + kpad];     // direction layer sees h8 through W'
     const int owner = r / G::kRowsB, rr = r - owner * G::kRowsB;
     const uint32_t part = G::kStepBytes * c.steps;                // bytes of one of {hi, lo} of a share
     unsigned char* base = chunks + (size_t)c.off * (G::kStepBytes * kParts * kCg) + (size_t)owner * part * kParts;
@@ -311,6 +337,11 @@ __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation
 template <int kCg>
 static int launch_pack_tc_cg(const ParamPtrsTc& pp, int precision, int new_activation, unsigned char* img,
                              cudaStream_t st) {
+  if (precision < SNB_PREC_F16X3 || precision > SNB_PREC_BF16)
+    return fail(SNB_ERR_INVALID, "launch_pack_tc: precision %d is not a tensor-core mode", precision);
+  float* fused = reinterpret_cast<float*>(img + sizeof(PackedHeader) + kConstBytes + chunks_bytes(precision));
+  fuse_bottleneck_kernel<<<148, 256, 0, st>>>(pp, fused);
+  if (int rc = check_launch("fuse_bottleneck_kernel")) return rc;
   if (precision == SNB_PREC_F16X3) pack_tc_kernel<false, true, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
   else if (precision == SNB_PREC_BF16X3) pack_tc_kernel<true, true, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
   else if (precision == SNB_PREC_BF16) pack_tc_kernel<true, false, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
@@ -389,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   const long long ntiles = (p.n_points + kTile - 1) / kTile;
   const long long n_groups = gridDim.x / kCg, group = blockIdx.x / kCg;
   const long long n_slots = ((ntiles + kCg - 1) / kCg + n_groups - 1) / n_groups;
-  const int n_layers_epi = p.sigma_only ? 8 : 9;   // layers with a TMEM->TMEM epilogue
+  const int n_layers_epi = 8;   // trunk layers with a TMEM->TMEM epilogue (the bottleneck is folded away)
   const int n_chunks = p.sigma_only ? tab.n_sigma_only : tab.n_total;
 
   // ---------------- one-time setup
@@ -675,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       // ---------------- trunk + bottleneck epilogues: D (TMEM) -> act -> A (TMEM)
       for (int l = 0; l < n_layers_epi; ++l) {
         const float* bias = s.cst + CL.b[l];
-        const bool relu = l < 8;
+        const bool relu = true;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3 && tid == 0;

@@ -15,13 +15,13 @@ assert lib.snb_debug_trace(buf, 2048) == 0
 t = list(buf)
 t0 = t[0]
 print("MMA warp: chunk: [loop top] [after A/enc waits] [after full wait] [after issue]   (cycles since slot start)")
-for ci in range(39):
+for ci in range(35):
     a, b, c, d = (t[ci * 4 + k] - t0 for k in range(4))
     print(f"  chunk {ci:2d}: {a:7d} {b:7d} (+{b - a:5d} wait A)  {c:7d} (+{c - b:5d} wait full)  {d:7d} (+{d - c:4d} issue)")
 print("epilogue warp 0: (layer, half): [start waiting d_full] [observed] [ld done] [q0 signalled] [q1 signalled]")
-for lh in range(18):
+for lh in range(16):
     e = [t[1024 + lh * 8 + k] - t0 for k in range(5)]
     print(f"  l={lh // 2} h={lh % 2}: wait_from {e[0]:7d}  d_full {e[1]:7d}  ld {e[2] - e[1]:5d}  q0 +{e[3] - e[1]:5d}  q1 +{e[4] - e[1]:5d}")
 e = [t[1024 + 18 * 8 + k] - t0 for k in range(5)]
 print(f"  dir layer: wait_from {e[0]:7d}  d_full {e[1]:7d}  drained +{e[2] - e[1]:5d}  math +{e[3] - e[1]:5d}  head/out +{e[4] - e[1]:5d}")
-print(f"  slot length (MMA warp, chunk 0 top -> chunk 38 issued): {t[38 * 4 + 3] - t0}")
+print(f"  slot length (MMA warp, chunk 0 top -> chunk 34 issued): {t[34 * 4 + 3] - t0}")
