@@ -332,7 +332,9 @@ def main():
         # the kernel is timed alone but in a back-to-back loop of tens of ms each: the power-capped
         # ("sustained") cuBLAS figure is the comparable denominator
         tensor_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
-        passes = 3 if precision.endswith("x3") else 1
+        # tensor-core modes fold the 256x256 bottleneck into the direction layer at pack time, so they
+        # execute (593408 - 65536) MACs per point and product; the split modes issue 3 products
+        passes = (3 if precision.endswith("x3") else 1) * (593408 - 65536) / 593408
         traffic = None
         tp = os.path.join(ROOT, "profiles", "field_traffic.json")
         if os.path.exists(tp):
@@ -361,7 +363,7 @@ def main():
                          "peak_source": f"MEASURED_PEAKS.json ({peaks['_source']}), dense bf16 cuBLAS, sustained",
                          "ms_per_launch": kern_ms,
                          "flops": "algorithmic 2*593408 per point (SURVEY 8d); "
-                                  + ("executed MMA flops are 3x (hi*hi + hi*lo + lo*hi)" if precision.endswith("x3")
+                                  + ("executed MMA flops: 3 products (hi*hi + hi*lo + lo*hi) x 0.89 (bottleneck folded into the dir layer)" if precision.endswith("x3")
                                      else "FFMA pipe, not tensor cores" if precision == "fp32" else "single pass")},
         }
         if not args.no_cpu_baseline and world == 1:
