@@ -53,9 +53,9 @@ using namespace umma;
 // ------------------------------------------------------------------ geometry
 constexpr int kTile = 128;             // points per CTA tile (MMA M = 128 * cta_group)
 constexpr int kNh = 128;               // output columns per MMA (N); a 256-wide layer is two halves
-constexpr int kEpiWarps = 8;           // warps 0..7: prologue / epilogue (2 per TMEM lane quadrant)
-constexpr int kMmaWarp = 8, kLoadWarp = 9;
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 16;          // warps 0..15: prologue / epilogue (4 per TMEM lane quadrant)
+constexpr int kMmaWarp = 16, kLoadWarp = 17;
+constexpr int kThreads = 576;          // <= 113 registers per thread
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
 
 // per cta_group geometry: a chunk is 128 output rows x (16 * steps) of K, steps <= kMaxSteps; each
@@ -367,7 +367,8 @@ struct TcSmem {
   alignas(128) unsigned char enc[kParts][kTile * kXyzPad * 2];   // canonical [k8][row][8] hi (, lo)
   alignas(128) unsigned char dir[kParts][kTile * kDirPad * 2];
   alignas(16) float cst[kConstFloats];
-  float part[2][4][kTile];        // head partial sums [column half][sigma,r,g,b][row]
+  float sigp[4][kTile];           // sigma head partial sums per 32-column group; [0] ends up holding sigma
+  // (the rgb head's partial sums alias dir[0], idle by then: float [4][3][kTile])
   uint64_t full[16], empty[16];
   uint64_t d_full[2], a_ready[4], a_free, enc_ready, dir_ready, d_drained;
   uint32_t tmem_base;
@@ -391,7 +392,7 @@ constexpr int kTraceLen = 2048;
 __device__ long long g_trace[kTraceLen];
 __device__ __forceinline__ void trace(bool on, int idx) { if (on && idx < kTraceLen) g_trace[idx] = clock64(); }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // canonical (SWIZZLE_NONE, K-major) byte offset of element (row, k) in a [k8][128 rows][8] block
 __device__ __forceinline__ uint32_t canon_off(int row, int k) { return (uint32_t)(k >> 3) * (kTile * 16) + row * 16 + (k & 7) * 2; }
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     // at the leader and count the epilogue threads of every CTA of the group
     for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], (kCg == 2 && leader) ? 2 : 1); mbar_init(&s.empty[i], 1); }
     mbar_init(&s.d_full[0], 1); mbar_init(&s.d_full[1], 1); mbar_init(&s.a_free, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&s.a_ready[i], kEpiWarps * 32 * kCg);
+    for (int i = 0; i < 4; ++i) mbar_init(&s.a_ready[i], kEpiWarps * 16 * kCg);   // the two warps-of-four that own the quarter
     mbar_init(&s.enc_ready, kEpiWarps * 32 * kCg);
     mbar_init(&s.dir_ready, kEpiWarps * 32 * kCg);
     mbar_init(&s.d_drained, kEpiWarps * 32 * kCg);
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     }
   } else {
     // ======================= prologue / epilogue warps =======================
-    const int quad = warp & 3, ch = warp >> 2;       // TMEM lane quadrant, column half
+    const int quad = warp & 3, ch = warp >> 2;       // TMEM lane quadrant, 32-column group (0..3) of a 128-column half
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     // hand-off to the MMA issuer, which lives in the leader CTA
@@ -619,36 +620,39 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       if (kSplit) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
     };
     auto tile_of = [&](long long slot) { return (group + slot * n_groups) * kCg + cta_rank; };
-    // 16 consecutive channels [c_lo, c_lo+16) of Embedding(3, L)(x): [x(3), sin(2^0 x)(3), cos(2^0 x)(3),
+    // 8 consecutive channels [c_lo, c_lo+8) of Embedding(3, L)(x): [x(3), sin(2^0 x)(3), cos(2^0 x)(3),
     // sin(2^1 x)(3), ...] (nerf.py:36-41), one sincosf per (frequency, coordinate) that the window touches
-    auto embed16 = [&](const float (&x)[3], int c_lo, int n_ch, int n_freqs, float (&v)[16]) {
+    auto embed8 = [&](const float (&x)[3], int c_lo, int n_ch, int n_freqs, float (&v)[8]) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = (c_lo + j < 3) ? x[(c_lo + j) % 3] : 0.f;   // identity / zero pad
+      for (int j = 0; j < 8; ++j) v[j] = (c_lo + j < 3) ? x[(c_lo + j) % 3] : 0.f;   // identity / zero pad
       for (int f = 0; f < n_freqs; ++f) {
         const int base = 3 + 6 * f;
-        if (base + 6 <= c_lo || base >= c_lo + 16) continue;
+        if (base + 6 <= c_lo || base >= c_lo + 8) continue;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const int js = base + c - c_lo, jc = js + 3;
-          if ((js >= 0 && js < 16) || (jc >= 0 && jc < 16)) {
+          if ((js >= 0 && js < 8) || (jc >= 0 && jc < 8)) {
             float sn, cs;
             sincosf(x[c] * (float)(1 << f), &sn, &cs);
-            if (js >= 0 && js < 16) v[js] = sn;
-            if (jc >= 0 && jc < 16 && base + 3 + c < n_ch) v[jc] = cs;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {           // static indices keep v[] in registers
+              if (j == js) v[j] = sn;
+              if (j == jc && base + 3 + c < n_ch) v[j] = cs;
+            }
           }
         }
       }
     };
-    // xyz embedding of one tile: this thread writes 32 of the 64 channels of its row (two parts of 16,
-    // so the work can be spread over two idle windows)
+    // xyz embedding of one tile: this thread writes 16 of the 64 channels of its row, in two parts of 8
+    // (so the work can be spread over two idle windows)
     auto encode_xyz = [&](long long slot, int part) {
       const long long pt = tile_of(slot) * kTile + row;
-      const int c_lo = (ch * 4 + part * 2) * 8;
-      float v[16];
+      const int c_lo = (ch * 2 + part) * 8;
+      float v[8];
       if (kEmbedded) {
         const float* xr = p.x + pt * p.x_stride;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (pt < p.n_points && c_lo + j < kXyzCh) ? xr[c_lo + j] : 0.f;
+        for (int j = 0; j < 8; ++j) v[j] = (pt < p.n_points && c_lo + j < kXyzCh) ? xr[c_lo + j] : 0.f;
       } else {
         float x[3] = {0.f, 0.f, 0.f};
         if (pt < p.n_points) {
@@ -660,12 +664,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           x[1] = __fadd_rn(r0.y, __fmul_rn(r1.x, zz));
           x[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, zz));
         }
-        embed16(x, c_lo, kXyzCh, SNB_XYZ_FREQS, v);
+        embed8(x, c_lo, kXyzCh, SNB_XYZ_FREQS, v);
       }
-      const float va[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
-      const float vb[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
-      put8(s.enc[0], s.enc[kSplit ? 1 : 0], c_lo / 8, va);
-      put8(s.enc[0], s.enc[kSplit ? 1 : 0], c_lo / 8 + 1, vb);
+      put8(s.enc[0], s.enc[kSplit ? 1 : 0], c_lo / 8, v);
       if (part == 1) {
         fence_proxy_async_smem();     // generic-proxy smem writes -> visible to tcgen05.mma
         signal(&s.enc_ready);
@@ -673,13 +674,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     };
     auto encode_dir = [&](long long slot) {
       const long long pt = tile_of(slot) * kTile + row;
-      const int c_lo = ch * 16;
-      float v[16];
+      const int c_lo = ch * 8;
+      float v[8];
       if (kEmbedded) {
         const int nin = p.sigma_only ? kXyzCh : kXyzCh + kDirCh;
         const float* xr = p.x + pt * p.x_stride;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
+        for (int j = 0; j < 8; ++j)
           v[j] = (pt < p.n_points && c_lo + j < kDirCh && kXyzCh + c_lo + j < nin) ? xr[kXyzCh + c_lo + j] : 0.f;
       } else {
         float d[3] = {0.f, 0.f, 0.f};
@@ -687,12 +688,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           const long long ray = pt / p.n_samples;
           d[0] = p.rays[ray * 8 + 3]; d[1] = p.rays[ray * 8 + 4]; d[2] = p.rays[ray * 8 + 5];
         }
-        embed16(d, c_lo, kDirCh, SNB_DIR_FREQS, v);
+        embed8(d, c_lo, kDirCh, SNB_DIR_FREQS, v);
       }
-      const float va[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
-      const float vb[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
-      put8(s.dir[0], s.dir[kSplit ? 1 : 0], c_lo / 8, va);
-      put8(s.dir[0], s.dir[kSplit ? 1 : 0], c_lo / 8 + 1, vb);
+      put8(s.dir[0], s.dir[kSplit ? 1 : 0], c_lo / 8, v);
       fence_proxy_async_smem();
       signal(&s.dir_ready);
     };
@@ -715,65 +713,47 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           mbar_wait(&s.d_full[h], ph_d[h]); ph_d[h] ^= 1;
           tc_fence_after();
           trace(tr, tb + 1);
+          const int q = ch >> 1;                       // the 64-column quarter this thread's group belongs to
+          const int c0 = h * kNh + ch * 32;            // output columns == next layer's k
           if (p.debug & 2) {
             if (h == 0) { mbar_wait(&s.a_free, ph_free); ph_free ^= 1; }
-            tc_fence_before(); signal(&s.a_ready[h * 2]); signal(&s.a_ready[h * 2 + 1]); continue;
+            tc_fence_before(); signal(&s.a_ready[h * 2 + q]); continue;
           }
-          // drain this accumulator half into registers (both 64-column quarters), then finish the
-          // quarters one at a time so the next layer's first K chunks can start early
-          uint32_t v[2][32];
-          tmem_ld32(tbase + lane_base + kColD + h * kNh + ch * 32, v[0]);
-          tmem_ld32(tbase + lane_base + kColD + h * kNh + 64 + ch * 32, v[1]);
+          uint32_t v[32];
+          tmem_ld32(tbase + lane_base + kColD + c0, v);
           tmem_wait_ld();
           trace(tr, tb + 2);
-          // bias + activation + hi/lo split of one 32-column group, in place: v[2j] = hi pair j,
-          // v[2j+1] = lo pair j (columns c0+2j, c0+2j+1)
-          auto finish_group = [&](uint32_t (&vv)[32], int c0, auto relu_tag, auto sigma_tag) {
+          // bias + activation + hi/lo split, in place: v[2j] = hi pair j, v[2j+1] = lo pair j
+          auto finish_group = [&](auto relu_tag, auto sigma_tag) {
             constexpr bool kRelu = decltype(relu_tag)::value, kSigma = decltype(sigma_tag)::value;
             const float2* b2 = reinterpret_cast<const float2*>(bias + c0);
             const float2* w2 = reinterpret_cast<const float2*>(s.cst + CL.sigma_w + c0);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 bb = b2[j];
-              float x0 = __uint_as_float(vv[2 * j]) + bb.x;
-              float x1 = __uint_as_float(vv[2 * j + 1]) + bb.y;
+              float x0 = __uint_as_float(v[2 * j]) + bb.x;
+              float x1 = __uint_as_float(v[2 * j + 1]) + bb.y;
               if (kRelu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
               if (kSigma) { const float2 ww = w2[j]; sig_part = fmaf(x0, ww.x, sig_part); sig_part = fmaf(x1, ww.y, sig_part); }
-              split_pair<kBf16, kSplit, kRelu>(x0, x1, vv[2 * j], vv[2 * j + 1]);
+              split_pair<kBf16, kSplit, kRelu>(x0, x1, v[2 * j], v[2 * j + 1]);
             }
           };
-          auto finish = [&](uint32_t (&vv)[32], int c0) {
-            if (l == 7) finish_group(vv, c0, std::true_type{}, std::true_type{});
-            else if (relu) finish_group(vv, c0, std::true_type{}, std::false_type{});
-            else finish_group(vv, c0, std::false_type{}, std::false_type{});
-          };
-          auto store_group = [&](uint32_t (&vv)[32], int c0, int q) {
+          if (l == 7) finish_group(std::true_type{}, std::true_type{});
+          else finish_group(std::true_type{}, std::false_type{});
+          // half a's results go to A[k 0..127], which this layer's (b,k0) MMAs still read: the math above
+          // overlaps both b phases, the stores wait until those MMAs have retired (a_free); half b's
+          // target A[k 128..255] is idle
+          if (h == 0) { mbar_wait(&s.a_free, ph_free); ph_free ^= 1; tc_fence_after(); }
+          {
             uint32_t phi[16], plo[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { phi[j] = vv[2 * j]; plo[j] = vv[2 * j + 1]; }
+            for (int j = 0; j < 16; ++j) { phi[j] = v[2 * j]; plo[j] = v[2 * j + 1]; }
             tmem_st16(tbase + lane_base + kColAhi + (c0 >> 1), phi);
             if (kSplit) tmem_st16(tbase + lane_base + kColAlo + (c0 >> 1), plo);
             tmem_wait_st();
             tc_fence_before();
             signal(&s.a_ready[h * 2 + q]);
             trace(tr, tb + 3 + q);
-          };
-          const int c00 = h * kNh + ch * 32, c01 = h * kNh + 64 + ch * 32;   // output columns == next layer's k
-          if (h == 0) {
-            // half a's results go to A[k 0..127], which this layer's (b,k0) MMAs still read: finish
-            // the math now (it overlaps both b phases), hold the stores until they have retired
-            finish(v[0], c00);
-            finish(v[1], c01);
-            mbar_wait(&s.a_free, ph_free); ph_free ^= 1;
-            tc_fence_after();
-            store_group(v[0], c00, 0);
-            store_group(v[1], c01, 1);
-          } else {
-            // half b's target A[k 128..255] is idle: deliver each quarter as soon as it is done
-            finish(v[0], c00);
-            store_group(v[0], c00, 0);
-            finish(v[1], c01);
-            store_group(v[1], c01, 1);
           }
         }
         // ---- background work in the idle window before this layer's next accumulator half is ready
@@ -782,11 +762,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
         if (l == 6 && slot + 1 < n_slots) encode_xyz(slot + 1, 1);            // (skip) MMAs have retired
         if (l == 7) {
           // sigma head (nerf.py:136): combine the two column halves of each row
-          s.part[ch][0][row] = sig_part;
+          s.sigp[ch][row] = sig_part;
           epi_bar_sync();
           if (ch == 0) {
-            const float sg = s.part[0][0][row] + s.part[1][0][row] + s.cst[CL.sigma_b];
-            s.part[0][0][row] = sg;      // keep for the final float4
+            const float sg = ((s.sigp[0][row] + s.sigp[1][row]) + (s.sigp[2][row] + s.sigp[3][row])) + s.cst[CL.sigma_b];
+            s.sigp[0][row] = sg;         // keep for the final float4
             if (p.sigma_only && pt < p.n_points) p.out[pt] = sg;
           }
           epi_bar_sync();
@@ -804,16 +784,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
         trace(tr, tb + 1);
         const float* bias = s.cst + CL.b[9];
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        uint32_t v[2][32];
-        tmem_ld32(tbase + lane_base + kColD + ch * 32, v[0]);
-        tmem_ld32(tbase + lane_base + kColD + 64 + ch * 32, v[1]);
+        uint32_t v[32];
+        const int c0 = ch * 32;
+        tmem_ld32(tbase + lane_base + kColD + c0, v);
         tmem_wait_ld();
         tc_fence_before();
         signal(&s.d_drained);      // D[0,128) is in registers: the next slot's layer 1 may overwrite it
         trace(tr, tb + 2);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int c0 = g * 64 + ch * 32;
+        {
           const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
           const float4* w0 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + c0);
           const float4* w1 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + kHalf + c0);
@@ -823,8 +801,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
             const float4 bb = b4[j4], r0 = w0[j4], r1 = w1[j4], r2 = w2[j4];
             // shifted softplus: fold the -1 into the bias
             const float sh = new_activation ? 1.0f : 0.0f;
-            float x[4] = {__uint_as_float(v[g][4 * j4]) + (bb.x - sh), __uint_as_float(v[g][4 * j4 + 1]) + (bb.y - sh),
-                          __uint_as_float(v[g][4 * j4 + 2]) + (bb.z - sh), __uint_as_float(v[g][4 * j4 + 3]) + (bb.w - sh)};
+            float x[4] = {__uint_as_float(v[4 * j4]) + (bb.x - sh), __uint_as_float(v[4 * j4 + 1]) + (bb.y - sh),
+                          __uint_as_float(v[4 * j4 + 2]) + (bb.z - sh), __uint_as_float(v[4 * j4 + 3]) + (bb.w - sh)};
             if (new_activation) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) x[e] = softplus_fast(x[e]);
@@ -838,16 +816,20 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           }
         }
         trace(tr, tb + 3);
-        s.part[ch][1][row] = a0; s.part[ch][2][row] = a1; s.part[ch][3][row] = a2;
+        // rgb partial sums go through the dir-embedding buffer: its last readers (this slot's dir-layer
+        // MMAs) have retired, and the next slot's encode_dir runs after the barrier below
+        float* rgbp = reinterpret_cast<float*>(s.dir[0]);     // [4][3][kTile]
+        rgbp[(ch * 3 + 0) * kTile + row] = a0; rgbp[(ch * 3 + 1) * kTile + row] = a1; rgbp[(ch * 3 + 2) * kTile + row] = a2;
         epi_bar_sync();
         if (ch == 0 && pt < p.n_points) {
           float c[3];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const float x = s.part[0][1 + k][row] + s.part[1][1 + k][row] + s.cst[CL.rgb_b + k];
+            const float x = ((rgbp[k * kTile + row] + rgbp[(3 + k) * kTile + row]) +
+                             (rgbp[(6 + k) * kTile + row] + rgbp[(9 + k) * kTile + row])) + s.cst[CL.rgb_b + k];
             c[k] = new_activation ? widened_sigmoid_f(x) : sigmoid_f(x);
           }
-          reinterpret_cast<float4*>(p.out)[pt] = make_float4(c[0], c[1], c[2], s.part[0][0][row]);
+          reinterpret_cast<float4*>(p.out)[pt] = make_float4(c[0], c[1], c[2], s.sigp[0][row]);
         }
         epi_bar_sync();
         trace(tr, tb + 4);

@@ -92,6 +92,43 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
   }
 }
 
+// C == 3 with a compile-time number of frequencies (the two embeddings SinNeRF uses): no integer
+// divisions, one sincosf per (row, frequency, coordinate).
+template <int L>
+__global__ void __launch_bounds__(256) embed3_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  constexpr int W = 3 * (2 * L + 1);
+  __shared__ __align__(16) float tile[kEmbedRows * W];
+  const long long nblocks = (n + kEmbedRows - 1) / kEmbedRows;
+  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const long long r0 = blk * kEmbedRows;
+    const int rows = (int)((n - r0) < kEmbedRows ? (n - r0) : kEmbedRows);
+    // item = (frequency slot f in 0..L, row r): thread handles one row's three coordinates at slot f
+    for (int it = threadIdx.x; it < (L + 1) * kEmbedRows; it += 256) {
+      const int f = it >> 7, r = it & (kEmbedRows - 1);
+      if (r >= rows) continue;
+      const float vx = x[(r0 + r) * 3], vy = x[(r0 + r) * 3 + 1], vz = x[(r0 + r) * 3 + 2];
+      float* t = tile + r * W;
+      if (f == 0) {
+        t[0] = vx; t[1] = vy; t[2] = vz;
+      } else {
+        const float sc = (float)(1 << (f - 1));
+        float s0, c0, s1, c1, s2, c2;
+        sincosf(vx * sc, &s0, &c0); sincosf(vy * sc, &s1, &c1); sincosf(vz * sc, &s2, &c2);
+        float* o = t + 3 + (f - 1) * 6;
+        o[0] = s0; o[1] = s1; o[2] = s2; o[3] = c0; o[4] = c1; o[5] = c2;
+      }
+    }
+    __syncthreads();
+    const long long base = r0 * W;          // kEmbedRows * W * 4 B per block keeps 16-byte alignment
+    const int nflt = rows * W, nvec = nflt >> 2;
+    float4* o4 = reinterpret_cast<float4*>(out + base);
+    const float4* t4 = reinterpret_cast<const float4*>(tile);
+    for (int v = threadIdx.x; v < nvec; v += 256) o4[v] = t4[v];
+    for (int v = (nvec << 2) + threadIdx.x; v < nflt; v += 256) out[base + v] = tile[v];
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // composite_fwd: read 16 B (rgb sigma) + 4 B (z) [+4 B noise] per point, write 4 B (w) per
 // point, + 32 B in (ray) and 16 B out (rgb, depth) per ray  ->  24 B/point + 48 B/ray.
@@ -364,15 +401,36 @@ __global__ void __launch_bounds__(128) importance_merge_kernel(
       if (z_new_out != nullptr) z_new_out[ray * Ni + j] = zn;
     }
     __syncwarp();
-    // sorted union (torch.sort(cat([z, z_new]))): rank of every element among all F
-    for (int i = lane; i < F; i += 32) {
-      const float v = zs[i];
-      int rank = 0;
-      for (int k = 0; k < F; ++k) {
-        const float o = zs[k];
-        rank += (o < v) || (o == v && k < i);
+    // sorted union (torch.sort(cat([z, z_new]))).  The coarse depths are sorted; the new ones are
+    // rank-sorted first (random u: any order; det u: already monotone up to an ulp at bin edges).
+    // Then every element's position is its own index plus a binary-search count in the other list
+    // (ties: coarse first).  O(Ni^2 + F log F) instead of the O(F^2) all-pairs rank.
+    float* zn = zs + S;
+    {
+      float mine[8];                       // Ni <= 256
+      int rk[8];
+      int cnt = 0;
+      for (int j = lane; j < Ni; j += 32, ++cnt) {
+        const float v = zn[j];
+        int r = 0;
+        for (int k = 0; k < Ni; ++k) { const float o = zn[k]; r += (o < v) || (o == v && k < j); }
+        mine[cnt] = v; rk[cnt] = r;
       }
-      z_fine[ray * F + rank] = v;
+      __syncwarp();
+      for (int c = 0; c < cnt; ++c) zn[rk[c]] = mine[c];
+      __syncwarp();
+    }
+    for (int i = lane; i < S; i += 32) {           // coarse element: + #{new < z}
+      const float v = zs[i];
+      int lo = 0, hi = Ni;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (zn[mid] < v) lo = mid + 1; else hi = mid; }
+      z_fine[ray * F + i + lo] = v;
+    }
+    for (int j = lane; j < Ni; j += 32) {          // new element: + #{coarse <= z}
+      const float v = zn[j];
+      int lo = 0, hi = S;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (zs[mid] <= v) lo = mid + 1; else hi = mid; }
+      z_fine[ray * F + j + lo] = v;
     }
     __syncwarp();
   }
@@ -450,6 +508,12 @@ int launch_sample_coarse(const float* rays, const float* z_steps, const float* p
 
 int launch_embed(const float* x, int64_t n, int C, int L, float* out, cudaStream_t st) {
   if (n == 0) return SNB_OK;
+  if (C == 3 && (L == SNB_XYZ_FREQS || L == SNB_DIR_FREQS) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int grid3 = grid_for(n, kEmbedRows, device_sms() * 6);
+    if (L == SNB_XYZ_FREQS) embed3_kernel<SNB_XYZ_FREQS><<<grid3, 256, 0, st>>>(x, n, out);
+    else embed3_kernel<SNB_DIR_FREQS><<<grid3, 256, 0, st>>>(x, n, out);
+    return check_launch("embed3_kernel");
+  }
   const size_t smem = (size_t)kEmbedRows * C * (2 * L + 1) * sizeof(float);
   if (smem > 200 * 1024) return fail(SNB_ERR_UNSUPPORTED, "snb_embed: C*(2L+1) too large for the smem tile");
   static size_t configured = 0;
@@ -507,6 +571,7 @@ int launch_importance_merge(const float* z_coarse, const float* w_coarse, const 
                             int64_t n_rays, int S, int Ni, float eps, float* z_fine, float* z_new,
                             cudaStream_t st) {
   if (n_rays == 0) return SNB_OK;
+  if (Ni > 256) return fail(SNB_ERR_UNSUPPORTED, "snb_importance_merge: N_importance > 256 (%d)", Ni);
   const size_t smem = (size_t)4 * ((S - 1) + (S + Ni)) * sizeof(float);
   if (smem > 48 * 1024) return fail(SNB_ERR_UNSUPPORTED, "snb_importance_merge: S+Ni too large");
   const int grid = grid_for(n_rays, 4, device_sms() * 16);
