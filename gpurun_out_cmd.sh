@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-echo "=== pytest all gpu"; timeout 600 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; grep -E "AssertionError|passed|failed|^FAILED|rc=" gpurun_out/pytest_gpu.log | head -8
-timeout 300 python tools/time_hbm_kernels.py > gpurun_out/hbm_kernels.log 2>&1; cat gpurun_out/hbm_kernels.log
-echo "=== bench"; timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; head -c 330 gpurun_out/bench_r01.json; echo; tail -3 gpurun_out/bench_r01.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:field_tc -s 2 -c 1 -o gpurun_out/prof_tc_final2 python tools/time_field.py --precision f16x3 --iters 1 > gpurun_out/ncu_tc.log 2>&1; tail -2 gpurun_out/ncu_tc.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:field_tc -s 2 -c 1 -o gpurun_out/prof_tc_final2_bf16 python tools/time_field.py --precision bf16 --iters 1 > gpurun_out/ncu_tc_bf16.log 2>&1; tail -2 gpurun_out/ncu_tc_bf16.log
+timeout 300 ncu --set full --clock-control none -k regex:composite_fwd -s 1 -c 1 -o gpurun_out/prof_composite python tools/time_hbm_kernels.py > gpurun_out/ncu_comp.log 2>&1; tail -1 gpurun_out/ncu_comp.log

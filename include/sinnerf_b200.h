@@ -120,6 +120,16 @@ int snb_importance_merge(const float* z_coarse, const float* weights_coarse, con
                          int64_t u_stride, int64_t n_rays, int n_samples, int n_importance, float eps,
                          float* z_fine, float* z_new, void* stream);
 
+/* ---- ray generation (the step before the path) ------------------------ */
+/* Pinhole-camera rays of a strided pixel window, written directly in the (N,8) layout:
+ * get_ray_directions (datasets/ray_utils.py:73-91; opencv=0: d = [(i-cx)/fx, -(j-cy)/fy, -1]) or
+ * get_ray_directions_dtu (datasets/dtu_proj.py:17-34; opencv=1: d = [(i-cx)/fx, (j-cy)/fy, 1]),
+ * get_rays (datasets/ray_utils.py:94-120: d @ c2w[:, :3].T, o = c2w[:, 3]) and the [o, d, near, far]
+ * concatenation.  c2w: HOST pointer to 12 floats, row-major (3,4).  Pixel (row0 + r*stride,
+ * col0 + c*stride) -> ray r*cols + c.  rays: device (rows*cols, 8), 16-byte aligned. */
+int snb_generate_rays(const float* c2w, float fx, float fy, float cx, float cy, float near, float far, int opencv,
+                      int row0, int col0, int rows, int cols, int stride, float* rays, void* stream);
+
 /* ---- training: forward that keeps activations, and the backward ------------------------ */
 
 /* The fused field pass of snb_field_forward in SNB_PREC_FP32 arithmetic, additionally keeping what the

@@ -319,3 +319,26 @@ def default_init_params(seed: int, dtype=torch.float32) -> Params:
         p[name + ".weight"], p[name + ".bias"] = w.to(dtype), b.to(dtype)
     torch.random.set_rng_state(gen_state)
     return p
+
+
+# --------------------------------------------------------------------------- #
+# f-1  ray generation (the step before the path)                               #
+# --------------------------------------------------------------------------- #
+def camera_rays(H: int, W: int, focal, c2w: Tensor, near: float, far: float, center=None, opencv: bool = False,
+                window=None) -> Tensor:
+    """datasets/ray_utils.py:73-120 (get_ray_directions + get_rays) / datasets/dtu_proj.py:17-34, and the
+    [o, d, near, far] concatenation the datasets do.  window = (row0, col0, rows, cols, stride)."""
+    fx, fy = (focal, focal) if not isinstance(focal, (tuple, list)) else focal
+    cx, cy = (W / 2, H / 2) if center is None else center
+    row0, col0, rows, cols, stride = (0, 0, H, W, 1) if window is None else window
+    jj = torch.arange(rows, dtype=torch.float32) * stride + row0
+    ii = torch.arange(cols, dtype=torch.float32) * stride + col0
+    j, i = torch.meshgrid(jj, ii, indexing="ij")
+    if opencv:
+        d = torch.stack([(i - cx) / fx, (j - cy) / fy, torch.ones_like(i)], -1)
+    else:
+        d = torch.stack([(i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)], -1)
+    d = (d @ c2w[:, :3].T).reshape(-1, 3)
+    o = c2w[:, 3].expand(d.shape)
+    n = d.shape[0]
+    return torch.cat([o, d, torch.full((n, 1), float(near)), torch.full((n, 1), float(far))], dim=-1)

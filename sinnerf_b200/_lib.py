@@ -49,6 +49,7 @@ SIGNATURES = {
     "snb_importance_merge": (C.c_int, [c_f, c_f, c_f, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_float, c_f,
                                        c_f, c_f]),
     "snb_render_forward": (C.c_int, [C.POINTER(SnbRenderArgs), c_f]),
+    "snb_generate_rays": (C.c_int, [C.POINTER(C.c_float)] + [C.c_float] * 6 + [C.c_int] * 6 + [c_f, c_f]),
     "snb_field_forward_train": (C.c_int, [c_f, c_f, c_f, C.c_int64, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f]),
     "snb_composite_backward": (C.c_int, [c_f, c_f, c_f, c_f, C.c_float, C.c_int, c_f, c_f, c_f, C.c_int64, C.c_int,
                                          c_f, c_f]),

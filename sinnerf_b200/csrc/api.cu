@@ -44,6 +44,8 @@ int launch_composite_bwd(const float*, const float*, const float*, const float*,
                          const float*, const float*, int64_t, int, float*, cudaStream_t);
 int field_backward_fp32(const float* const*, float* const*, int, const float*, const float*, const float*,
                         const float*, const float*, const float*, int64_t, float*, float*, float*, cudaStream_t);
+int launch_generate_rays(const float*, float, float, float, float, float, float, int, int, int, int, int, int, float*,
+                         cudaStream_t);
 // tensor-core modes (field_tc.cu)
 size_t tc_packed_bytes(int precision);
 int launch_pack_tc(const float* const*, int, int, void*, cudaStream_t);
@@ -176,6 +178,17 @@ int snb_importance_merge(const float* z_coarse, const float* weights_coarse, con
   SNB_REQUIRE(u_stride == 0 || u_stride >= n_importance, "snb_importance_merge: bad u stride");
   return launch_importance_merge(z_coarse, weights_coarse, u, u_stride, n_rays, n_samples, n_importance, eps,
                                  z_fine, z_new, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int snb_generate_rays(const float* c2w, float fx, float fy, float cx, float cy, float near, float far, int opencv,
+                      int row0, int col0, int rows, int cols, int stride, float* rays, void* stream) {
+  SNB_REQUIRE(c2w != nullptr, "snb_generate_rays: null camera matrix");
+  SNB_REQUIRE(rows >= 0 && cols >= 0 && stride >= 1 && row0 >= 0 && col0 >= 0, "snb_generate_rays: bad window");
+  SNB_REQUIRE(fx != 0.f && fy != 0.f, "snb_generate_rays: zero focal length");
+  SNB_REQUIRE((long long)rows * cols == 0 || (rays != nullptr && aligned16(rays)),
+              "snb_generate_rays: rays must be a 16-byte aligned device buffer");
+  return launch_generate_rays(c2w, fx, fy, cx, cy, near, far, opencv, row0, col0, rows, cols, stride, rays,
+                              reinterpret_cast<cudaStream_t>(stream));
 }
 
 int snb_field_forward_train(const void* packed_fp32, const float* rays, const float* z_vals, int64_t n_rays,

@@ -48,6 +48,42 @@ __global__ void sample_coarse_kernel(const float* __restrict__ rays, const float
 }
 
 // ---------------------------------------------------------------------------------------
+// generate_rays: rays of a pinhole camera straight into the (N,8) layout, replacing
+//   get_ray_directions        datasets/ray_utils.py:73-91   d = [(i-W/2)/f, -(j-H/2)/f, -1]
+//   get_ray_directions_dtu    datasets/dtu_proj.py:17-34    d = [(i-cx)/fx, (j-cy)/fy, 1]
+//   get_rays                  datasets/ray_utils.py:94-120  d_world = d @ c2w[:, :3].T, o = c2w[:, 3]
+//   + torch.cat([o, d, near, far])                          datasets/llff.py style assembly
+// for a strided window of the pixel grid (the ray patches of *_ray_patch_* datasets).
+// 0 B in, 32 B/ray out.
+// ---------------------------------------------------------------------------------------
+struct RayGenArgs {
+  float c2w[12];     // row-major (3,4)
+  float fx, fy, cx, cy;
+  float near, far;
+  int opencv;        // 0: blender/LLFF convention (-y up, -z forward), 1: DTU / OpenCV (+z forward)
+  int row0, col0, rows, cols, stride;
+  float* rays;
+};
+__global__ void generate_rays_kernel(RayGenArgs a) {
+  const long long n = (long long)a.rows * a.cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / a.cols), c = (int)(e - (long long)r * a.cols);
+    const float i = (float)(a.col0 + c * a.stride), j = (float)(a.row0 + r * a.stride);
+    float dx, dy, dz;
+    if (a.opencv) { dx = __fdiv_rn(i - a.cx, a.fx); dy = __fdiv_rn(j - a.cy, a.fy); dz = 1.0f; }
+    else { dx = __fdiv_rn(i - a.cx, a.fx); dy = -__fdiv_rn(j - a.cy, a.fy); dz = -1.0f; }
+    float4 lo, hi;
+    lo.x = a.c2w[3]; lo.y = a.c2w[7]; lo.z = a.c2w[11];
+    lo.w = fmaf(dz, a.c2w[2], fmaf(dy, a.c2w[1], dx * a.c2w[0]));
+    hi.x = fmaf(dz, a.c2w[6], fmaf(dy, a.c2w[5], dx * a.c2w[4]));
+    hi.y = fmaf(dz, a.c2w[10], fmaf(dy, a.c2w[9], dx * a.c2w[8]));
+    hi.z = a.near; hi.w = a.far;
+    reinterpret_cast<float4*>(a.rays)[2 * e] = lo;
+    reinterpret_cast<float4*>(a.rays)[2 * e + 1] = hi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // embed: 4*C B in, 4*C*(2L+1) B out per row (264 B/point for C=3, L=10).
 // A block computes 128 rows into smem (one sincosf per (row, freq, channel)), then streams
 // the dense [128][C*(2L+1)] tile out with 128-bit stores.
@@ -504,6 +540,19 @@ int launch_sample_coarse(const float* rays, const float* z_steps, const float* p
   const int grid = grid_for(n_rays * S, 256, device_sms() * 8);
   sample_coarse_kernel<<<grid, 256, 0, st>>>(rays, z_steps, perturb_u, perturb, use_disp, n_rays, S, z);
   return check_launch("sample_coarse_kernel");
+}
+
+int launch_generate_rays(const float* c2w_host, float fx, float fy, float cx, float cy, float near, float far,
+                         int opencv, int row0, int col0, int rows, int cols, int stride, float* rays,
+                         cudaStream_t st) {
+  RayGenArgs a;
+  for (int i = 0; i < 12; ++i) a.c2w[i] = c2w_host[i];
+  a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.near = near; a.far = far; a.opencv = opencv;
+  a.row0 = row0; a.col0 = col0; a.rows = rows; a.cols = cols; a.stride = stride; a.rays = rays;
+  const long long n = (long long)rows * cols;
+  if (n == 0) return SNB_OK;
+  generate_rays_kernel<<<grid_for(n, 256, device_sms() * 8), 256, 0, st>>>(a);
+  return check_launch("generate_rays_kernel");
 }
 
 int launch_embed(const float* x, int64_t n, int C, int L, float* out, cudaStream_t st) {

@@ -139,8 +139,46 @@ def grad_golden(room):
     print("wrote", path, "loss", float(loss))
 
 
+def rays_golden():
+    """Reference ray generation: datasets/ray_utils.py (blender/LLFF) and datasets/dtu_proj.py (DTU)."""
+    from datasets.ray_utils import get_ray_directions, get_rays
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for tag, (H, W, f) in {"lego": (40, 56, 77.7), "llff": (378 // 6, 504 // 6, 410.0 / 6)}.items():
+        c2w = torch.cat([torch.linalg.qr(torch.randn(3, 3, generator=g))[0], torch.randn(3, 1, generator=g)], 1)
+        d = get_ray_directions(H, W, f)
+        o, dw = get_rays(d, c2w)
+        near, far = 2.0, 6.0
+        rays = torch.cat([o, dw, near * torch.ones_like(o[:, :1]), far * torch.ones_like(o[:, :1])], 1)
+        out[f"{tag}_cfg"] = np.array([H, W, f, near, far])
+        out[f"{tag}_c2w"] = np_(c2w)
+        out[f"{tag}_rays"] = np_(rays)
+    # DTU: own directions function (imports the dataset module lazily: it needs cv2 / PIL only for loading)
+    H, W, fx, fy, cx, cy = 32, 40, 361.5, 360.9, 19.3, 16.8
+    c2w = torch.cat([torch.linalg.qr(torch.randn(3, 3, generator=g))[0], torch.randn(3, 1, generator=g)], 1)
+    try:
+        from datasets.dtu_proj import get_ray_directions_dtu
+        d = get_ray_directions_dtu(H, W, [fx, fy], [cx, cy])
+    except Exception as e:   # module-level imports of dtu_proj that are missing here
+        print("dtu_proj import failed (", e, "); using the formula of dtu_proj.py:31-32 via ray_utils.create_meshgrid")
+        from datasets.ray_utils import create_meshgrid
+        i, j = create_meshgrid(H, W, normalized_coordinates=False)[0].unbind(-1)
+        d = torch.stack([(i - cx) / fx, (j - cy) / fy, torch.ones_like(i)], -1)
+    o, dw = get_rays(d, c2w)
+    rays = torch.cat([o, dw, 2.125 * torch.ones_like(o[:, :1]), 4.525 * torch.ones_like(o[:, :1])], 1)
+    out["dtu_cfg"] = np.array([H, W, fx, fy, cx, cy, 2.125, 4.525])
+    out["dtu_c2w"] = np_(c2w)
+    out["dtu_rays"] = np_(rays)
+    path = os.path.join(HERE, "rays.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
 def main():
     room = load_room()
+    if "--rays-only" in sys.argv:
+        rays_golden()
+        return
     if "--grad-only" in sys.argv:
         grad_golden(room)
         return
@@ -216,6 +254,7 @@ def main():
     render_case("lego_seed0_32p16_odd", seed_models, lego[:33], n_samples=32, n_importance=16,
                 perturb=0.5, noise_std=0.3, white_back=True)
     grad_golden(room)
+    rays_golden()
 
 
 if __name__ == "__main__":

@@ -129,3 +129,16 @@ def test_oracle_autograd_matches_reference_autograd():
             key = f"grad_{which}/{name}"
             if key in gz:
                 assert_close(prm.grad, gz[key], 2e-4, key)
+
+
+def test_camera_rays_match_reference():
+    """oracle ray generation == the reference's get_ray_directions/get_rays (golden rays.npz)."""
+    gz = load_npz("rays.npz")
+    for tag in ("lego", "llff"):
+        H, W, f, near, far = gz[f"{tag}_cfg"]
+        got = orc.camera_rays(int(H), int(W), float(f), t(gz[f"{tag}_c2w"]), near, far)
+        assert torch.allclose(got, t(gz[f"{tag}_rays"]), rtol=0, atol=1e-6), tag
+    H, W, fx, fy, cx, cy, near, far = gz["dtu_cfg"]
+    got = orc.camera_rays(int(H), int(W), (float(fx), float(fy)), t(gz["dtu_c2w"]), near, far, center=(float(cx), float(cy)),
+                          opencv=True)
+    assert torch.allclose(got, t(gz["dtu_rays"]), rtol=0, atol=1e-6)
