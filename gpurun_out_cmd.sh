@@ -1,2 +1,7 @@
 mkdir -p gpurun_out
-echo "=== pytest all gpu"; timeout 600 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; grep -E "AssertionError|Error|passed|failed|^FAILED|rc=" gpurun_out/pytest_gpu.log | head -12
+timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
+for pr in f16x3 bf16x3 bf16; do timeout 120 python tools/time_field.py --precision $pr --iters 5; done > gpurun_out/timing_v11.log 2>&1
+timeout 120 python tools/time_field.py --precision f16x3 --samples 64 --sigma-only --iters 5 >> gpurun_out/timing_v11.log 2>&1
+cat gpurun_out/timing_v11.log
+timeout 120 python tools/trace_field.py bf16 > gpurun_out/trace_bf16_v11.log 2>&1
+timeout 120 python tools/trace_field.py f16x3 > gpurun_out/trace_f16x3_v11.log 2>&1

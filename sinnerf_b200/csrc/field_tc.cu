@@ -43,6 +43,7 @@
 #include <stdlib.h>
 
 #include <type_traits>
+#include <utility>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -157,6 +158,31 @@ static_assert(h_chunks_cg2.n_total == 35 && h_chunks_cg2.n_sigma_only == 32, "ch
 static_assert(h_chunks_cg1.steps_total == h_chunks_cg2.steps_total && h_chunks_cg1.steps_total == 258, "K16 steps per tile");
 template <int kCg>
 __device__ __forceinline__ const ChunkTable& chunk_table() { return kCg == 2 ? c_chunks_cg2 : c_chunks_cg1; }
+
+// number of waits on barrier code `code` (WAIT_*) in chunks [0, ci) -- plus chunk ci's own `wait` when
+// the question is about its mid-chunk wait.  a_ready[q] completes once per layer epilogue, 8 per
+// slot, so (prior_waits & 1) is the parity to wait for.
+__host__ __device__ constexpr int prior_waits(const ChunkTable& t, int ci, int code, bool for_mid) {
+  int n = 0;
+  for (int i = 0; i < ci; ++i) n += (t.c[i].wait == code) + (t.c[i].wait_mid == code);
+  if (for_mid) n += t.c[ci].wait == code;
+  return n;
+}
+__host__ __device__ constexpr bool wait_counts_ok(const ChunkTable& t) {
+  for (int q = 0; q < 4; ++q) {
+    if (prior_waits(t, t.n_total, WAIT_A0 + q, false) != 8) return false;       // layers 1..7 and the dir layer
+    if (prior_waits(t, t.n_sigma_only, WAIT_A0 + q, false) != 7) return false;  // + the explicit drain of layer 8's
+  }
+  return prior_waits(t, t.n_total, WAIT_ENC, false) == 1 && prior_waits(t, t.n_total, WAIT_DIR, false) == 1;
+}
+static_assert(wait_counts_ok(h_chunks_cg2), "static wait parities");
+
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
 
 // cta_group used by the tensor-core path.  The kernels stay templated on it (Geo<1> is the
 // single-CTA geometry the CTA-pair design was derived from) but only pairs are instantiated.
@@ -477,127 +503,126 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     }
   } else if (warp == kMmaWarp) {
     // ======================= MMA issuer (leader CTA) =======================
-    // The whole warp walks the chunk schedule (uniform control flow); one elected lane issues
-    // the tcgen05 instructions of a chunk, so they compile to single uniform-datapath ops.
-    const uint32_t idesc = make_idesc(kBf16 ? kFmtBF16 : kFmtF16, kTile * kCg, kNh);
-    const uint32_t enc_hi = smem_u32(s.enc[0]), dir_hi = smem_u32(s.dir[0]);
-    const uint32_t enc_lo = smem_u32(s.enc[kSplit ? 1 : 0]), dir_lo = smem_u32(s.dir[kSplit ? 1 : 0]);
-    const uint32_t ring0 = smem_u32(s.ring[0]);
-    // descriptor templates: only the 14-bit start-address field changes between MMAs
-    const uint64_t desc_b0 = make_smem_desc(0, G::kRowsB * 16, 128);
-    const uint64_t desc_a0 = make_smem_desc(0, kTile * 16, 128);
-    constexpr uint32_t kStepB = (2 * G::kRowsB * 16) >> 4;     // one K16 step inside a chunk, in 16-B units
-    constexpr uint32_t kStepA = (2 * kTile * 16) >> 4;
-    auto wait_bar = [&](uint64_t* bar, uint32_t ph) { mbar_wait(bar, ph); };
-    auto issue_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) {
-      if (kCg == 2) mma2_ts(d, a, b, idesc, acc); else mma_ts(d, a, b, idesc, acc);
-    };
-    auto issue_ss = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
-      if (kCg == 2) mma2_ss(d, a, b, idesc, acc); else mma_ss(d, a, b, idesc, acc);
-    };
-    auto commit = [&](uint64_t* bar) { if (kCg == 2) mma2_commit(bar); else mma_commit(bar); };
-    uint32_t it = 0, ph_a = 0, ph_enc = 0, ph_dir = 0, ph_drain = 0;   // ph_a: bit q = parity of a_ready[q]
-    for (long long slot = 0; slot < n_slots; ++slot) {
-      Chunk c_next = tab.c[0];
-      for (int ci = 0; ci < n_chunks; ++ci, ++it) {
-        const Chunk c = c_next;
-        c_next = tab.c[ci + 1 < n_chunks ? ci + 1 : 0];   // prefetch the next entry (constant-cache latency)
-        const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3 && lane == 0;
-        trace(tr, ci * 4 + 0);
-        auto wait_code = [&](int w) {
-          if (w == WAIT_ENC) { wait_bar(&s.enc_ready, ph_enc); ph_enc ^= 1; }
-          else if (w == WAIT_DIR) { wait_bar(&s.dir_ready, ph_dir); ph_dir ^= 1; }
-          else if (w >= WAIT_A0) { const int q = w - WAIT_A0; wait_bar(&s.a_ready[q], (ph_a >> q) & 1); ph_a ^= 1u << q; }
-        };
-        wait_code(c.wait);
-        const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-        trace(tr, ci * 4 + 1);
-        wait_bar(&s.full[st], ph);
-        tc_fence_after();
-        trace(tr, ci * 4 + 2);
-        const uint32_t d = tbase + kColD + (c.layer == 9 ? 0 : c.half * kNh);
-        // descriptors as (lo, hi) words: only the start-address field in the low word moves
-        const uint32_t bd_hi32 = (uint32_t)(desc_b0 >> 32), ad_hi32 = (uint32_t)(desc_a0 >> 32);
-        const uint32_t bh = (uint32_t)desc_b0 + ((ring0 + st * kStageBytes) >> 4);       // W_hi block
-        const uint32_t bl = bh + ((G::kStepBytes * c.steps) >> 4);                         // W_lo block
-        // K16 steps [kLo, kHi) of this chunk, fully unrolled (compile-time ranges: no per-step predicates)
-        auto issue_range = [&](auto lo_tag, auto hi_tag) {
-          constexpr int kLo = decltype(lo_tag)::value, kHi = decltype(hi_tag)::value;
-          if (c.src == SRC_HID) {
-            const uint32_t a_hi = tbase + kColAhi + (uint32_t)c.a16 * 8;
-            const uint32_t a_lo = tbase + kColAlo + (uint32_t)c.a16 * 8;
-#pragma unroll
-            for (int ks = kLo; ks < kHi; ++ks) {
-              const uint32_t acc = (ks == 0 && c.first) ? 0u : 1u;
-              if (kCg == 2) {
-                mma2_ts_lohi(d, a_hi + ks * 8, bh + ks * kStepB, bd_hi32, idesc, acc);
-                if (kSplit) {
-                  mma2_ts_lohi(d, a_lo + ks * 8, bh + ks * kStepB, bd_hi32, idesc, 1);
-                  mma2_ts_lohi(d, a_hi + ks * 8, bl + ks * kStepB, bd_hi32, idesc, 1);
-                }
-              } else {
-                const uint64_t b1 = ((uint64_t)bd_hi32 << 32) | (bh + ks * kStepB), b2 = ((uint64_t)bd_hi32 << 32) | (bl + ks * kStepB);
-                mma_ts(d, a_hi + ks * 8, b1, idesc, acc);
-                if (kSplit) { mma_ts(d, a_lo + ks * 8, b1, idesc, 1); mma_ts(d, a_hi + ks * 8, b2, idesc, 1); }
-              }
-            }
-          } else {
-            const uint32_t a_off = (uint32_t)c.a16 * 2 * (kTile * 16);
-            const uint32_t ah = (uint32_t)desc_a0 + (((c.src == SRC_ENC ? enc_hi : dir_hi) + a_off) >> 4);
-            const uint32_t al = (uint32_t)desc_a0 + (((c.src == SRC_ENC ? enc_lo : dir_lo) + a_off) >> 4);
-#pragma unroll
-            for (int ks = kLo; ks < kHi; ++ks) {
-              const uint32_t acc = (ks == 0 && c.first) ? 0u : 1u;
-              if (kCg == 2) {
-                mma2_ss_lohi(d, ah + ks * kStepA, ad_hi32, bh + ks * kStepB, bd_hi32, idesc, acc);
-                if (kSplit) {
-                  mma2_ss_lohi(d, al + ks * kStepA, ad_hi32, bh + ks * kStepB, bd_hi32, idesc, 1);
-                  mma2_ss_lohi(d, ah + ks * kStepA, ad_hi32, bl + ks * kStepB, bd_hi32, idesc, 1);
-                }
-              } else {
-                const uint64_t a1 = ((uint64_t)ad_hi32 << 32) | (ah + ks * kStepA), a2 = ((uint64_t)ad_hi32 << 32) | (al + ks * kStepA);
-                const uint64_t b1 = ((uint64_t)bd_hi32 << 32) | (bh + ks * kStepB), b2 = ((uint64_t)bd_hi32 << 32) | (bl + ks * kStepB);
-                mma_ss(d, a1, b1, idesc, acc);
-                if (kSplit) { mma_ss(d, a2, b1, idesc, 1); mma_ss(d, a1, b2, idesc, 1); }
-              }
-            }
-          }
-        };
-        using I0 = std::integral_constant<int, 0>;
-        using IH = std::integral_constant<int, G::kMaxSteps / 2>;
-        using IF = std::integral_constant<int, G::kMaxSteps>;
-        using I2 = std::integral_constant<int, 2>;
-        const bool do_mma = !(p.debug & 4);
-        const bool two_part = c.mid < c.steps;          // only full chunks are split (at the K-quarter boundary)
-        if (elect_one() && do_mma) {
-          if (c.steps == G::kMaxSteps) { if (two_part) issue_range(I0{}, IH{}); else issue_range(I0{}, IF{}); }
-          else if (c.steps == G::kMaxSteps / 2) issue_range(I0{}, IH{});
-          else issue_range(I0{}, I2{});
-        }
-        __syncwarp();
-        if (two_part) {
-          wait_code(c.wait_mid);
+    // One elected lane runs the whole role.  The chunk schedule is unrolled at compile time
+    // (static_for over the constexpr table): every wait, operand offset, accumulate flag and
+    // commit of a chunk is an immediate, so a chunk costs a few dozen instructions besides its
+    // MMAs.  (Measured: the table-driven loop spent ~200 instructions / ~1000 cycles per chunk,
+    // more than the 515 cycles the tensor pipe needs for a bf16 chunk -- the issuer, not the
+    // pipe, set the pace; profiles/r01_timing_experiments.txt v11.)
+    if (elect_one()) {
+      constexpr ChunkTable T = make_chunk_table<G::kKc>();
+      const uint32_t idesc = make_idesc(kBf16 ? kFmtBF16 : kFmtF16, kTile * kCg, kNh);
+      const uint32_t enc_hi = smem_u32(s.enc[0]), dir_hi = smem_u32(s.dir[0]);
+      const uint32_t enc_lo = smem_u32(s.enc[kSplit ? 1 : 0]), dir_lo = smem_u32(s.dir[kSplit ? 1 : 0]);
+      // descriptors as (lo, hi) words: only the 14-bit start-address field in the low word moves
+      const uint64_t desc_b0 = make_smem_desc(0, G::kRowsB * 16, 128);
+      const uint64_t desc_a0 = make_smem_desc(0, kTile * 16, 128);
+      const uint32_t bd_hi32 = (uint32_t)(desc_b0 >> 32), ad_hi32 = (uint32_t)(desc_a0 >> 32);
+      const uint32_t b_ring0 = (uint32_t)desc_b0 + (smem_u32(s.ring[0]) >> 4);
+      const uint32_t a_enc_hi = (uint32_t)desc_a0 + (enc_hi >> 4), a_enc_lo = (uint32_t)desc_a0 + (enc_lo >> 4);
+      const uint32_t a_dir_hi = (uint32_t)desc_a0 + (dir_hi >> 4), a_dir_lo = (uint32_t)desc_a0 + (dir_lo >> 4);
+      constexpr uint32_t kStepB = (2 * G::kRowsB * 16) >> 4;     // one K16 step inside a chunk, in 16-B units
+      constexpr uint32_t kStepA = (2 * kTile * 16) >> 4;
+      auto commit = [&](uint64_t* bar) { if (kCg == 2) mma2_commit(bar); else mma_commit(bar); };
+      const bool do_mma = !(p.debug & 4);
+      uint32_t st = 0, ph_full = 0;            // ring position: stage and the parity of its `full` barrier
+      for (long long slot = 0; slot < n_slots; ++slot) {
+        const uint32_t slot_par = (uint32_t)slot & 1;    // enc_ready / dir_ready / d_drained complete once per slot
+        const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3;
+        static_for<T.n_total>([&](auto tag) {
+          constexpr int CI = decltype(tag)::value;
+          constexpr Chunk c = T.c[CI];
+          if (CI >= T.n_sigma_only && p.sigma_only) return;
+          trace(tr, CI * 4 + 0);
+          // a_ready[q] completes 8 times per slot (static_assert below): the parity of each wait is static
+          auto wait_code = [&](auto code_tag, auto mid_tag) {
+            constexpr int w = decltype(code_tag)::value;
+            if (w == WAIT_ENC) mbar_wait(&s.enc_ready, slot_par);
+            else if (w == WAIT_DIR) mbar_wait(&s.dir_ready, slot_par);
+            else if (w >= WAIT_A0) mbar_wait(&s.a_ready[w - WAIT_A0], prior_waits(T, CI, w, decltype(mid_tag)::value) & 1);
+          };
+          wait_code(std::integral_constant<int, c.wait>{}, std::false_type{});
+          trace(tr, CI * 4 + 1);
+          mbar_wait(&s.full[st], ph_full);
           tc_fence_after();
-          if (elect_one() && do_mma) issue_range(IH{}, IF{});
-          __syncwarp();
-        }
-        if (elect_one()) {
+          trace(tr, CI * 4 + 2);
+          const uint32_t d = tbase + kColD + (c.layer == 9 ? 0 : c.half * kNh);
+          const uint32_t bh = b_ring0 + st * (kStageBytes >> 4);           // W_hi block
+          const uint32_t bl = bh + ((G::kStepBytes * c.steps) >> 4);        // W_lo block
+          // K16 steps [kLo, kHi) of this chunk
+          auto issue_range = [&](auto lo_tag, auto hi_tag) {
+            constexpr int kLo = decltype(lo_tag)::value, kHi = decltype(hi_tag)::value;
+            if (c.src == SRC_HID) {
+              const uint32_t a_hi = tbase + kColAhi + (uint32_t)c.a16 * 8;
+              const uint32_t a_lo = tbase + kColAlo + (uint32_t)c.a16 * 8;
+#pragma unroll
+              for (int ks = kLo; ks < kHi; ++ks) {
+                const uint32_t acc = (ks == 0 && c.first) ? 0u : 1u;
+                if (kCg == 2) {
+                  mma2_ts_lohi(d, a_hi + ks * 8, bh + ks * kStepB, bd_hi32, idesc, acc);
+                  if (kSplit) {
+                    mma2_ts_lohi(d, a_lo + ks * 8, bh + ks * kStepB, bd_hi32, idesc, 1);
+                    mma2_ts_lohi(d, a_hi + ks * 8, bl + ks * kStepB, bd_hi32, idesc, 1);
+                  }
+                } else {
+                  const uint64_t b1 = ((uint64_t)bd_hi32 << 32) | (bh + ks * kStepB), b2 = ((uint64_t)bd_hi32 << 32) | (bl + ks * kStepB);
+                  mma_ts(d, a_hi + ks * 8, b1, idesc, acc);
+                  if (kSplit) { mma_ts(d, a_lo + ks * 8, b1, idesc, 1); mma_ts(d, a_hi + ks * 8, b2, idesc, 1); }
+                }
+              }
+            } else {
+              constexpr uint32_t a_off = ((uint32_t)c.a16 * 2 * (kTile * 16)) >> 4;
+              const uint32_t ah = (c.src == SRC_ENC ? a_enc_hi : a_dir_hi) + a_off;
+              const uint32_t al = (c.src == SRC_ENC ? a_enc_lo : a_dir_lo) + a_off;
+#pragma unroll
+              for (int ks = kLo; ks < kHi; ++ks) {
+                const uint32_t acc = (ks == 0 && c.first) ? 0u : 1u;
+                if (kCg == 2) {
+                  mma2_ss_lohi(d, ah + ks * kStepA, ad_hi32, bh + ks * kStepB, bd_hi32, idesc, acc);
+                  if (kSplit) {
+                    mma2_ss_lohi(d, al + ks * kStepA, ad_hi32, bh + ks * kStepB, bd_hi32, idesc, 1);
+                    mma2_ss_lohi(d, ah + ks * kStepA, ad_hi32, bl + ks * kStepB, bd_hi32, idesc, 1);
+                  }
+                } else {
+                  const uint64_t a1 = ((uint64_t)ad_hi32 << 32) | (ah + ks * kStepA), a2 = ((uint64_t)ad_hi32 << 32) | (al + ks * kStepA);
+                  const uint64_t b1 = ((uint64_t)bd_hi32 << 32) | (bh + ks * kStepB), b2 = ((uint64_t)bd_hi32 << 32) | (bl + ks * kStepB);
+                  mma_ss(d, a1, b1, idesc, acc);
+                  if (kSplit) { mma_ss(d, a2, b1, idesc, 1); mma_ss(d, a1, b2, idesc, 1); }
+                }
+              }
+            }
+          };
+          using I0 = std::integral_constant<int, 0>;
+          using IM = std::integral_constant<int, c.mid>;
+          using IS = std::integral_constant<int, c.steps>;
+          if (do_mma) issue_range(I0{}, IM{});
+          trace(tr, 512 + CI * 4 + 0);
+          if (c.mid < c.steps) {            // the chunk spans two K quarters: the second arrives later
+            wait_code(std::integral_constant<int, c.wait_mid>{}, std::true_type{});
+            tc_fence_after();
+            if (do_mma) issue_range(IM{}, IS{});
+            trace(tr, 512 + CI * 4 + 1);
+          }
           commit(&s.empty[st]);        // ring slot free (in both CTAs of a pair) once these MMAs retire
+          trace(tr, 512 + CI * 4 + 2);
           if (c.commit & COMMIT_AFREE) commit(&s.a_free);
           if (c.commit & COMMIT_D0) commit(&s.d_full[0]);
           if (c.commit & COMMIT_D1) commit(&s.d_full[1]);
+          trace(tr, 512 + CI * 4 + 3);
+          if (++st == kStages) { st = 0; ph_full ^= 1; }
+          trace(tr, CI * 4 + 3);
+        });
+        if (p.sigma_only) {
+          // layer 8's epilogue arrives on a_ready[0..3] with nobody waiting: consume the phases
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mbar_wait(&s.a_ready[q], prior_waits(T, T.n_sigma_only, WAIT_A0 + q, false) & 1);
+        } else {
+          // the next slot's layer 1 overwrites D[0,128): wait until the dir-layer epilogue has read it
+          mbar_wait(&s.d_drained, slot_par);
         }
-        __syncwarp();
-        trace(tr, ci * 4 + 3);
-      }
-      if (p.sigma_only) {
-        // layer 8's epilogue arrives on a_ready[0..3] with nobody waiting: consume the phases
-        for (int q = 0; q < 4; ++q) { wait_bar(&s.a_ready[q], (ph_a >> q) & 1); ph_a ^= 1u << q; }
-      } else {
-        // the next slot's layer 1 overwrites D[0,128): wait until the dir-layer epilogue has read it
-        wait_bar(&s.d_drained, ph_drain); ph_drain ^= 1;
       }
     }
+    __syncwarp();
   } else {
     // ======================= prologue / epilogue warps =======================
     const int quad = warp & 3, ch = warp >> 2;       // TMEM lane quadrant, 32-column group (0..3) of a 128-column half
@@ -605,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     // hand-off to the MMA issuer, which lives in the leader CTA
     auto signal = [&](uint64_t* bar) { if (kCg == 2 && !leader) mbar_arrive_remote(bar, 0); else mbar_arrive(bar); };
-    uint32_t ph_d[2] = {0, 0}, ph_free = 0;
+    uint32_t ph_d = 0, ph_free = 0;       // ph_d: bit h = parity of d_full[h]
 
     // ---- positional encodings of one tile -> smem (canonical, hi/lo).  Split in pieces so they
     // fit the epilogue warps' idle windows: xyz part 0 (identity + 3 of this thread's 5
@@ -710,7 +735,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3 && tid == 0;
           const int tb = 1024 + (l * 2 + h) * 8;
           trace(tr, tb + 0);
-          mbar_wait(&s.d_full[h], ph_d[h]); ph_d[h] ^= 1;
+          mbar_wait(&s.d_full[h], (ph_d >> h) & 1); ph_d ^= 1u << h;
           tc_fence_after();
           trace(tr, tb + 1);
           const int q = ch >> 1;                       // the 64-column quarter this thread's group belongs to
@@ -779,7 +804,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
         const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3 && tid == 0;
         const int tb = 1024 + 18 * 8;
         trace(tr, tb + 0);
-        mbar_wait(&s.d_full[0], ph_d[0]); ph_d[0] ^= 1;
+        mbar_wait(&s.d_full[0], ph_d & 1); ph_d ^= 1u;
         tc_fence_after();
         trace(tr, tb + 1);
         const float* bias = s.cst + CL.b[9];

@@ -5,7 +5,7 @@ import os
 import subprocess
 import sys
 
-os.environ["SNB_TC_DEBUG"] = "8"
+os.environ["SNB_TC_DEBUG"] = str(8 | int(os.environ.get("SNB_TC_DEBUG_EXTRA", "0")))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.argv = [sys.argv[0], "--precision", sys.argv[1] if len(sys.argv) > 1 else "f16x3", "--rays", "8000", "--iters", "1"]
 exec(open(os.path.join(os.path.dirname(__file__), "time_field.py")).read())
@@ -17,7 +17,10 @@ t0 = t[0]
 print("MMA warp: chunk: [loop top] [after A/enc waits] [after full wait] [after issue]   (cycles since slot start)")
 for ci in range(35):
     a, b, c, d = (t[ci * 4 + k] - t0 for k in range(4))
-    print(f"  chunk {ci:2d}: {a:7d} {b:7d} (+{b - a:5d} wait A)  {c:7d} (+{c - b:5d} wait full)  {d:7d} (+{d - c:4d} issue)")
+    i0, i1, c0, c1 = (t[512 + ci * 4 + k] - t0 for k in range(4))
+    two = i1 > 0 and i1 > i0
+    print(f"  chunk {ci:2d}: {a:7d} {b:7d} (+{b - a:5d} wait A)  {c:7d} (+{c - b:5d} wait full)  {d:7d} (+{d - c:4d} issue)"
+          f"   [mma part0 +{i0 - c:4d}" + (f", part1 at +{i1 - c:4d}" if two else "") + f", commit empty +{c0 - c:4d}, commits done +{c1 - c:4d}]")
 print("epilogue warp 0: (layer, half): [start waiting d_full] [observed] [ld done] [q0 signalled] [q1 signalled]")
 for lh in range(16):
     e = [t[1024 + lh * 8 + k] - t0 for k in range(5)]
