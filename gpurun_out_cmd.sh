@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
-for pr in f16x3 bf16x3 bf16; do timeout 120 python tools/time_field.py --precision $pr --iters 5; done > gpurun_out/timing_v11.log 2>&1
-timeout 120 python tools/time_field.py --precision f16x3 --samples 64 --sigma-only --iters 5 >> gpurun_out/timing_v11.log 2>&1
-cat gpurun_out/timing_v11.log
-timeout 120 python tools/trace_field.py bf16 > gpurun_out/trace_bf16_v11.log 2>&1
-timeout 120 python tools/trace_field.py f16x3 > gpurun_out/trace_f16x3_v11.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_backward.py -m gpu -q -x > gpurun_out/pytest_bwd.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_bwd.log; grep -E "Error|passed|failed|rc=" gpurun_out/pytest_bwd.log | head -20
+timeout 200 python tools/time_train.py > gpurun_out/train_tcw.log 2>&1; cat gpurun_out/train_tcw.log | tail -1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train.csv python tools/time_train.py --iters 1 > gpurun_out/ncu_train.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_train.csv | head -12

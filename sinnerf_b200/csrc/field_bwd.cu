@@ -12,6 +12,8 @@
 // cp.async copies; wgrad accumulates a 128x128 block of dW per CTA in registers over a slice of
 // P and finishes with atomics (split-P), dgrad is the forward tiling with W used untransposed.
 // Roofline: FP32 FFMA pipe, 2x the forward FLOPs; HBM ~7 KB/point/layer.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace snb {
@@ -316,8 +318,15 @@ static int dev_sms() {
   return sms;
 }
 
+// wgrad_tc.cu: the same contraction on tensor cores (bf16 hi/lo split, fp32 accumulate in TMEM)
+int run_wgrad_tc(const float* dY, int N, const float* X, int ldx, int K, float* dW, int ldw, int col_off, float* db,
+                 long long P, cudaStream_t st);
+
 static int run_wgrad(const float* dY, int N, const float* X, int ldx, int K, float* dW, int ldw, int col_off,
                      float* db, long long P, cudaStream_t st) {
+  // SNB_BWD_SIMT=1 keeps the FFMA kernels (debugging / A-B timing); the tensor-core kernel is the default
+  static const bool simt = getenv("SNB_BWD_SIMT") && atoi(getenv("SNB_BWD_SIMT")) != 0;
+  if (!simt) return run_wgrad_tc(dY, N, X, ldx, K, dW, ldw, col_off, db, P, st);
   WgradArgs a{dY, N, X, ldx, K, dW, ldw, col_off, db, P, 0};
   const int nb = N / 128, kb = (K + 127) / 128;
   int splits = (2 * dev_sms()) / (nb * kb);
