@@ -132,13 +132,15 @@ int snb_generate_rays(const float* c2w, float fx, float fy, float cx, float cy, 
 
 /* ---- training: forward that keeps activations, and the backward ------------------------ */
 
-/* The fused field pass of snb_field_forward in SNB_PREC_FP32 arithmetic, additionally keeping what the
- * backward needs (the reference keeps the same tensors inside autograd): the two embeddings and every
- * layer's post-activation output, as plain row-major fp32 tensors.  P = n_rays * n_samples.
- *   save_enc (P,64)  save_dir (P,32)  save_h (9,P,256) [h1..h8, bottleneck]  save_g (P,128) */
-int snb_field_forward_train(const void* packed_fp32, const float* rays, const float* z_vals, int64_t n_rays,
-                            int n_samples, float* raw, float* save_enc, float* save_dir, float* save_h,
-                            float* save_g, void* stream);
+/* The fused field pass of snb_field_forward (same `packed` image / `precision` pairing), additionally
+ * keeping what the backward needs (the reference keeps the same tensors inside autograd): the two
+ * embeddings and every ReLU / direction layer's post-activation output, as plain row-major fp32
+ * tensors.  P = n_rays * n_samples.  The activation-free bottleneck (nerf.py:140) is not kept: the
+ * backward differentiates through the folded product Wd[:, :256] Wf instead.
+ *   save_enc (P,64)  save_dir (P,32)  save_h (8,P,256) [h1..h8]  save_g (P,128) */
+int snb_field_forward_train(const void* packed, int precision, const float* rays, const float* z_vals,
+                            int64_t n_rays, int n_samples, float* raw, float* save_enc, float* save_dir,
+                            float* save_h, float* save_g, void* stream);
 
 /* Backward of models/rendering.py:215-248 (closed form).  g_rgb (N,3), g_depth (N,),
  * g_weights (N,S) are dL/d(outputs), any may be NULL (= 0).  -> g_raw (N,S,4) = dL/d[rgb, sigma]. */
@@ -148,11 +150,13 @@ int snb_composite_backward(const float* raw, const float* z_vals, const float* r
 
 /* Backward of NeRF.forward (autograd through models/nerf.py:105-148) for one field pass.
  * params / grads: HOST arrays of 24 device pointers in state-dict order; grads are ACCUMULATED into
- * (zero them first).  ws_a, ws_b (P,256) and ws_s (P,128) are scratch.  No gradient reaches rays or z. */
+ * (zero them first).  Scratch: ws_a, ws_b (P,256), ws_s (P,128), ws_w (SNB_BWD_WS_FLOATS floats).
+ * No gradient reaches rays or z. */
+#define SNB_BWD_WS_FLOATS (2 * 128 * 256 + 128)
 int snb_field_backward(const float* const* params, float* const* grads, int new_activation,
                        const float* g_raw, const float* raw, const float* save_enc, const float* save_dir,
                        const float* save_h, const float* save_g, int64_t n_points, float* ws_a, float* ws_b,
-                       float* ws_s, void* stream);
+                       float* ws_s, float* ws_w, void* stream);
 
 /* ---- whole path -------------------------------------------------------------------- */
 typedef struct SnbRenderArgs {

@@ -50,12 +50,13 @@ SIGNATURES = {
                                        c_f, c_f]),
     "snb_render_forward": (C.c_int, [C.POINTER(SnbRenderArgs), c_f]),
     "snb_generate_rays": (C.c_int, [C.POINTER(C.c_float)] + [C.c_float] * 6 + [C.c_int] * 6 + [c_f, c_f]),
-    "snb_field_forward_train": (C.c_int, [c_f, c_f, c_f, C.c_int64, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "snb_field_forward_train": (C.c_int, [c_f, C.c_int, c_f, c_f, C.c_int64, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f]),
     "snb_composite_backward": (C.c_int, [c_f, c_f, c_f, c_f, C.c_float, C.c_int, c_f, c_f, c_f, C.c_int64, C.c_int,
                                          c_f, c_f]),
     "snb_field_backward": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, c_f, c_f, c_f, c_f, c_f,
-                                     c_f, C.c_int64, c_f, c_f, c_f, c_f]),
+                                     c_f, C.c_int64, c_f, c_f, c_f, c_f, c_f]),
 }
+BWD_WS_FLOATS = 2 * 128 * 256 + 128   # SNB_BWD_WS_FLOATS
 
 _lib = None
 

@@ -43,7 +43,8 @@ int field_forward_train_fp32(const void*, const float*, const float*, int64_t, i
 int launch_composite_bwd(const float*, const float*, const float*, const float*, float, int, const float*,
                          const float*, const float*, int64_t, int, float*, cudaStream_t);
 int field_backward_fp32(const float* const*, float* const*, int, const float*, const float*, const float*,
-                        const float*, const float*, const float*, int64_t, float*, float*, float*, cudaStream_t);
+                        const float*, const float*, const float*, int64_t, float*, float*, float*, float*,
+                        cudaStream_t);
 int launch_generate_rays(const float*, float, float, float, float, float, float, int, int, int, int, int, int, float*,
                          cudaStream_t);
 // tensor-core modes (field_tc.cu)
@@ -51,6 +52,8 @@ size_t tc_packed_bytes(int precision);
 int launch_pack_tc(const float* const*, int, int, void*, cudaStream_t);
 int field_forward_tc(const void*, int, const float*, const float*, int64_t, int, int, float*, cudaStream_t);
 int mlp_forward_tc(const void*, int, const float*, int64_t, int64_t, int, float*, cudaStream_t);
+int field_forward_train_tc(const void*, int, const float*, const float*, int64_t, int, float*, float*, float*, float*,
+                           float*, cudaStream_t);
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -191,16 +194,21 @@ int snb_generate_rays(const float* c2w, float fx, float fy, float cx, float cy, 
                               reinterpret_cast<cudaStream_t>(stream));
 }
 
-int snb_field_forward_train(const void* packed_fp32, const float* rays, const float* z_vals, int64_t n_rays,
-                            int n_samples, float* raw, float* save_enc, float* save_dir, float* save_h,
-                            float* save_g, void* stream) {
+int snb_field_forward_train(const void* packed, int precision, const float* rays, const float* z_vals,
+                            int64_t n_rays, int n_samples, float* raw, float* save_enc, float* save_dir,
+                            float* save_h, float* save_g, void* stream) {
+  if (int rc = check_precision(precision)) return rc;
   SNB_REQUIRE(n_rays >= 0 && n_samples >= 1, "snb_field_forward_train: bad extents");
-  SNB_REQUIRE(n_rays == 0 || (packed_fp32 && rays && z_vals && raw && save_enc && save_dir && save_h && save_g),
+  SNB_REQUIRE(n_rays == 0 || (packed && rays && z_vals && raw && save_enc && save_dir && save_h && save_g),
               "snb_field_forward_train: null pointer");
-  SNB_REQUIRE(aligned16(rays) && aligned16(raw) && aligned16(save_h) && aligned16(save_g),
+  SNB_REQUIRE(aligned16(rays) && aligned16(raw) && aligned16(save_enc) && aligned16(save_dir) && aligned16(save_h) &&
+                  aligned16(save_g),
               "snb_field_forward_train: buffers must be 16-byte aligned");
-  return field_forward_train_fp32(packed_fp32, rays, z_vals, n_rays, n_samples, raw, save_enc, save_dir, save_h,
-                                  save_g, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == SNB_PREC_FP32)
+    return field_forward_train_fp32(packed, rays, z_vals, n_rays, n_samples, raw, save_enc, save_dir, save_h, save_g, st);
+  return field_forward_train_tc(packed, precision, rays, z_vals, n_rays, n_samples, raw, save_enc, save_dir, save_h,
+                                save_g, st);
 }
 
 int snb_composite_backward(const float* raw, const float* z_vals, const float* rays, const float* noise,
@@ -217,15 +225,15 @@ int snb_composite_backward(const float* raw, const float* z_vals, const float* r
 int snb_field_backward(const float* const* params, float* const* grads, int new_activation, const float* g_raw,
                        const float* raw, const float* save_enc, const float* save_dir, const float* save_h,
                        const float* save_g, int64_t n_points, float* ws_a, float* ws_b, float* ws_s,
-                       void* stream) {
+                       float* ws_w, void* stream) {
   SNB_REQUIRE(n_points >= 0, "snb_field_backward: negative point count");
   SNB_REQUIRE(params && grads, "snb_field_backward: null parameter arrays");
   for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i)
     SNB_REQUIRE(params[i] && grads[i], "snb_field_backward: parameter / gradient tensor %d is null", i);
-  SNB_REQUIRE(n_points == 0 || (g_raw && raw && save_enc && save_dir && save_h && save_g && ws_a && ws_b && ws_s),
+  SNB_REQUIRE(n_points == 0 || (g_raw && raw && save_enc && save_dir && save_h && save_g && ws_a && ws_b && ws_s && ws_w),
               "snb_field_backward: null pointer");
   return field_backward_fp32(params, grads, new_activation, g_raw, raw, save_enc, save_dir, save_h, save_g,
-                             n_points, ws_a, ws_b, ws_s, reinterpret_cast<cudaStream_t>(stream));
+                             n_points, ws_a, ws_b, ws_s, ws_w, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int snb_render_forward(const SnbRenderArgs* a, void* stream) {

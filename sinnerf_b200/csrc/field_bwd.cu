@@ -356,13 +356,64 @@ static int run_dgrad(const float* dY, int N, const float* W, int ldw, int col_of
 }
 
 // params / grads: 24 device pointers in state-dict order (SNB_N_PARAM_TENSORS); grads are accumulated into.
+// ------------------------------------------------------------------------------------------
+// The bottleneck ("xyz_encoding_final", nerf.py:140) has no activation, so the direction layer sees
+//   s = Wd[:, :256] (Wf h8 + bf) + Wd[:, 256:] dir + bd = W' h8 + Wd[:, 256:] dir + b',  W' = Wd[:, :256] Wf
+// -- the forward kernels use exactly that (field_tc.cu folds W' at pack time), and so does the
+// backward: one wgrad against h8 gives dW' (128 x 256) and db' (128), and the chain rule through the
+// product is three tiny matrix products that do not depend on the number of points:
+//   dWd[:, :256] += dW' Wf^T + db' (x) bf     dWf += Wd[:, :256]^T dW'     dbf += Wd[:, :256]^T db'     dbd += db'
+// No per-point bottleneck activations, no P-sized wgrad / dgrad for that layer.
+// ------------------------------------------------------------------------------------------
+constexpr int kFoldW = 0, kFoldDW = kHalf * kWidth, kFoldDB = 2 * kHalf * kWidth;   // offsets into ws_w (floats)
+
+__global__ void fold_weights_kernel(const float* __restrict__ Wd, const float* __restrict__ Wf, float* __restrict__ ws) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kHalf * kWidth; e += gridDim.x * blockDim.x) {
+    const int n = e / kWidth, k = e - n * kWidth;
+    float acc = 0.f;
+    for (int j = 0; j < kWidth; ++j) acc = fmaf(Wd[n * 283 + j], Wf[j * kWidth + k], acc);
+    ws[kFoldW + e] = acc;
+    ws[kFoldDW + e] = 0.f;
+    if (e < kHalf) ws[kFoldDB + e] = 0.f;
+  }
+}
+
+__global__ void unfold_grads_kernel(const float* __restrict__ Wd, const float* __restrict__ Wf, const float* __restrict__ bf,
+                                    const float* __restrict__ ws, float* __restrict__ dWd, float* __restrict__ dbd,
+                                    float* __restrict__ dWf, float* __restrict__ dbf) {
+  const float* dWp = ws + kFoldDW;
+  const float* dbp = ws + kFoldDB;
+  const int n_a = kHalf * kWidth, n_b = kWidth * kWidth;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_a + n_b + kWidth + kHalf; e += gridDim.x * blockDim.x) {
+    if (e < n_a) {                       // dWd[n][j] += sum_k dW'[n][k] Wf[j][k] + db'[n] bf[j]
+      const int n = e / kWidth, j = e - n * kWidth;
+      float acc = dbp[n] * bf[j];
+      for (int k = 0; k < kWidth; ++k) acc = fmaf(dWp[n * kWidth + k], Wf[j * kWidth + k], acc);
+      dWd[n * 283 + j] += acc;
+    } else if (e < n_a + n_b) {          // dWf[j][k] += sum_n Wd[n][j] dW'[n][k]
+      const int f = e - n_a, j = f / kWidth, k = f - j * kWidth;
+      float acc = 0.f;
+      for (int n = 0; n < kHalf; ++n) acc = fmaf(Wd[n * 283 + j], dWp[n * kWidth + k], acc);
+      dWf[f] += acc;
+    } else if (e < n_a + n_b + kWidth) { // dbf[j] += sum_n Wd[n][j] db'[n]
+      const int j = e - n_a - n_b;
+      float acc = 0.f;
+      for (int n = 0; n < kHalf; ++n) acc = fmaf(Wd[n * 283 + j], dbp[n], acc);
+      dbf[j] += acc;
+    } else {
+      const int n = e - n_a - n_b - kWidth;
+      dbd[n] += dbp[n];
+    }
+  }
+}
+
 int field_backward_fp32(const float* const* params, float* const* grads, int new_activation, const float* g_raw,
                         const float* raw, const float* save_enc, const float* save_dir, const float* save_h,
-                        const float* save_g, int64_t n_points, float* ws_a, float* ws_b, float* ws_s,
+                        const float* save_g, int64_t n_points, float* ws_a, float* ws_b, float* ws_s, float* ws_w,
                         cudaStream_t st) {
   const long long P = n_points;
   if (P == 0) return SNB_OK;
-  auto H = [&](int l) { return save_h + (size_t)l * P * kWidth; };   // l = 0..7: h1..h8, 8: bottleneck
+  auto H = [&](int l) { return save_h + (size_t)l * P * kWidth; };   // l = 0..7: h1..h8
   int rc;
   // heads
   {
@@ -372,13 +423,16 @@ int field_backward_fp32(const float* const* params, float* const* grads, int new
     head_bwd_kernel<<<grid, 256, 0, st>>>(a);
     if ((rc = check_launch("head_bwd_kernel"))) return rc;
   }
-  // direction layer: X = [bottleneck | dir]
-  if ((rc = run_wgrad(ws_s, 128, H(8), 256, 256, grads[18], 283, 0, grads[19], P, st))) return rc;
+  // direction layer with the bottleneck folded in: X = [h8 (through W') | dir]
+  fold_weights_kernel<<<128, 256, 0, st>>>(params[18], params[16], ws_w);
+  if ((rc = check_launch("fold_weights_kernel"))) return rc;
+  if ((rc = run_wgrad(ws_s, 128, H(7), 256, 256, ws_w + kFoldDW, 256, 0, ws_w + kFoldDB, P, st))) return rc;
   if ((rc = run_wgrad(ws_s, 128, save_dir, kDirPad, kDirCh, grads[18], 283, 256, nullptr, P, st))) return rc;
-  if ((rc = run_dgrad(ws_s, 128, params[18], 283, 0, nullptr, nullptr, 0, nullptr, ws_a, P, st))) return rc;
-  // bottleneck: dY = ws_a (no activation); its input h8 also feeds sigma
-  if ((rc = run_wgrad(ws_a, 256, H(7), 256, 256, grads[16], 256, 0, grads[17], P, st))) return rc;
-  if ((rc = run_dgrad(ws_a, 256, params[16], 256, 0, H(7), g_raw + 3, 4, params[kSigmaW], ws_b, P, st))) return rc;
+  unfold_grads_kernel<<<392, 256, 0, st>>>(params[18], params[16], params[17], ws_w, grads[18], grads[19], grads[16],
+                                           grads[17]);
+  if ((rc = check_launch("unfold_grads_kernel"))) return rc;
+  // into h8: through W', plus the sigma head's term; ReLU mask of h8
+  if ((rc = run_dgrad(ws_s, 128, ws_w + kFoldW, 256, 0, H(7), g_raw + 3, 4, params[kSigmaW], ws_b, P, st))) return rc;
   // trunk layers 8..2 (index l = 7..1): dY lives in cur, dX goes to nxt
   float* cur = ws_b;
   float* nxt = ws_a;

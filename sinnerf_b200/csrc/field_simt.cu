@@ -160,7 +160,7 @@ struct FieldParams {
   // training forward (all nullable together): activations kept for field_bwd.cu
   float* save_enc;       // (P,64)  xyz embedding, pad column zero
   float* save_dir;       // (P,32)  dir embedding, pad columns zero
-  float* save_h;         // (9,P,256) h1..h8 (post-ReLU) and the bottleneck
+  float* save_h;         // (8,P,256) h1..h8 (post-ReLU)
   float* save_g;         // (P,128) direction layer output (post-activation)
 };
 
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_simt_kernel(FieldParams p) 
     if (p.sigma_only) continue;  // uniform across the CTA
 
     // ---------------- bottleneck (no activation) + direction layer ----------------
-    gemm_layer<256>(s, W + L.w[8], W + L.b[8], s.act, 256, nullptr, 0, ACT_NONE, s.act, save_ptr(8), p0, p.n_points);
+    gemm_layer<256>(s, W + L.w[8], W + L.b[8], s.act, 256, nullptr, 0, ACT_NONE, s.act, nullptr, p0, p.n_points);   // not kept: the backward folds this layer
     gemm_layer<128>(s, W + L.w[9], W + L.b[9], s.act, 256, s.dir, 32,
                     new_activation ? ACT_SOFTPLUS : ACT_RELU, s.act, saving ? p.save_g : nullptr, p0, p.n_points);
     // ---------------- rgb head ----------------

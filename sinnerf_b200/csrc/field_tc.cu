@@ -410,6 +410,11 @@ struct TcParams {
   long long n_points;
   int sigma_only;
   float* out;
+  // training forward (kTrain): what the backward needs, row-major fp32 (snb_field_forward_train)
+  float* save_enc;         // (P,64)
+  float* save_dir;         // (P,32)
+  float* save_h;           // (8,P,256)
+  float* save_g;           // (P,128)
   int debug;   // timing experiments only (SNB_TC_DEBUG): 2 = epilogue skips math, 4 = no MMAs
 };
 
@@ -423,8 +428,9 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;"
 // canonical (SWIZZLE_NONE, K-major) byte offset of element (row, k) in a [k8][128 rows][8] block
 __device__ __forceinline__ uint32_t canon_off(int row, int k) { return (uint32_t)(k >> 3) * (kTile * 16) + row * 16 + (k & 7) * 2; }
 
-template <bool kBf16, bool kSplit, bool kEmbedded, int kCg>
+template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, bool kTrain = false>
 __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
+  static_assert(!(kTrain && kEmbedded), "the training forward is the fused (rays, z) entry only");
   using Smem = TcSmem<kSplit, kCg>;
   using G = Geo<kCg>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -690,6 +696,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           x[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, zz));
         }
         embed8(x, c_lo, kXyzCh, SNB_XYZ_FREQS, v);
+        if (kTrain && pt < p.n_points) {
+          float4* dst = reinterpret_cast<float4*>(p.save_enc + pt * kXyzPad + c_lo);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]); dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
       }
       put8(s.enc[0], s.enc[kSplit ? 1 : 0], c_lo / 8, v);
       if (part == 1) {
@@ -714,6 +724,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           d[0] = p.rays[ray * 8 + 3]; d[1] = p.rays[ray * 8 + 4]; d[2] = p.rays[ray * 8 + 5];
         }
         embed8(d, c_lo, kDirCh, SNB_DIR_FREQS, v);
+        if (kTrain && pt < p.n_points) {
+          float4* dst = reinterpret_cast<float4*>(p.save_dir + pt * kDirPad + c_lo);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]); dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
       }
       put8(s.dir[0], s.dir[kSplit ? 1 : 0], c_lo / 8, v);
       fence_proxy_async_smem();
@@ -753,14 +767,24 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
             constexpr bool kRelu = decltype(relu_tag)::value, kSigma = decltype(sigma_tag)::value;
             const float2* b2 = reinterpret_cast<const float2*>(bias + c0);
             const float2* w2 = reinterpret_cast<const float2*>(s.cst + CL.sigma_w + c0);
+            float* save_row = kTrain ? p.save_h + ((size_t)l * p.n_points + pt) * kWidth + c0 : nullptr;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 bb = b2[j];
-              float x0 = __uint_as_float(v[2 * j]) + bb.x;
-              float x1 = __uint_as_float(v[2 * j + 1]) + bb.y;
-              if (kRelu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-              if (kSigma) { const float2 ww = w2[j]; sig_part = fmaf(x0, ww.x, sig_part); sig_part = fmaf(x1, ww.y, sig_part); }
-              split_pair<kBf16, kSplit, kRelu>(x0, x1, v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 16; j += 2) {
+              float x[4];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float2 bb = b2[j + e];
+                x[2 * e] = __uint_as_float(v[2 * (j + e)]) + bb.x;
+                x[2 * e + 1] = __uint_as_float(v[2 * (j + e) + 1]) + bb.y;
+                if (kRelu) { x[2 * e] = fmaxf(x[2 * e], 0.f); x[2 * e + 1] = fmaxf(x[2 * e + 1], 0.f); }
+                if (kSigma) {
+                  const float2 ww = w2[j + e];
+                  sig_part = fmaf(x[2 * e], ww.x, sig_part); sig_part = fmaf(x[2 * e + 1], ww.y, sig_part);
+                }
+              }
+              if (kTrain && pt < p.n_points) *reinterpret_cast<float4*>(save_row + 2 * j) = make_float4(x[0], x[1], x[2], x[3]);
+              split_pair<kBf16, kSplit, kRelu>(x[0], x[1], v[2 * j], v[2 * j + 1]);
+              split_pair<kBf16, kSplit, kRelu>(x[2], x[3], v[2 * j + 2], v[2 * j + 3]);
             }
           };
           if (l == 7) finish_group(std::true_type{}, std::true_type{});
@@ -835,6 +859,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
             }
+            if (kTrain && pt < p.n_points)
+              *reinterpret_cast<float4*>(p.save_g + pt * kHalf + c0 + 4 * j4) = make_float4(x[0], x[1], x[2], x[3]);
             a0 = fmaf(x[0], r0.x, a0); a0 = fmaf(x[1], r0.y, a0); a0 = fmaf(x[2], r0.z, a0); a0 = fmaf(x[3], r0.w, a0);
             a1 = fmaf(x[0], r1.x, a1); a1 = fmaf(x[1], r1.y, a1); a1 = fmaf(x[2], r1.z, a1); a1 = fmaf(x[3], r1.w, a1);
             a2 = fmaf(x[0], r2.x, a2); a2 = fmaf(x[1], r2.y, a2); a2 = fmaf(x[2], r2.z, a2); a2 = fmaf(x[3], r2.w, a2);
@@ -868,11 +894,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 }
 
 // ------------------------------------------------------------------ host
-template <bool kBf16, bool kSplit, bool kEmbedded, int kCg>
+template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, bool kTrain = false>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
   static bool configured = false;
   const size_t smem = sizeof(TcSmem<kSplit, kCg>) + 1024;
-  auto kern = field_tc_kernel<kBf16, kSplit, kEmbedded, kCg>;
+  auto kern = field_tc_kernel<kBf16, kSplit, kEmbedded, kCg, kTrain>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(field_tc): %s", cudaGetErrorString(e));
@@ -929,6 +955,23 @@ int field_forward_tc(const void* packed, int precision, const float* rays, const
   p.sigma_only = sigma_only;
   p.out = raw;
   return dispatch_tc<false>(precision, p, st);
+}
+
+int field_forward_train_tc(const void* packed, int precision, const float* rays, const float* z, int64_t n_rays,
+                           int n_samples, float* raw, float* save_enc, float* save_dir, float* save_h, float* save_g,
+                           cudaStream_t st) {
+  TcParams p{};
+  p.image = reinterpret_cast<const unsigned char*>(packed);
+  p.rays = rays; p.z = z; p.n_samples = n_samples;
+  p.n_points = (long long)n_rays * n_samples;
+  p.out = raw;
+  p.save_enc = save_enc; p.save_dir = save_dir; p.save_h = save_h; p.save_g = save_g;
+  switch (precision) {
+    case SNB_PREC_F16X3: return launch_tc<false, true, false, 2, true>(p, st);
+    case SNB_PREC_BF16X3: return launch_tc<true, true, false, 2, true>(p, st);
+    case SNB_PREC_BF16: return launch_tc<true, false, false, 2, true>(p, st);
+  }
+  return fail(SNB_ERR_INVALID, "precision %d is not a tensor-core mode", precision);
 }
 
 int mlp_forward_tc(const void* packed, int precision, const float* x, int64_t x_stride, int64_t n_points,

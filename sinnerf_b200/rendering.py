@@ -46,19 +46,19 @@ class _FieldPass(torch.autograd.Function):
     reference propagates nothing into rays / z either (rendering.py:311-313)."""
 
     @staticmethod
-    def forward(ctx, model: "NeRF", rays, z, *params):
+    def forward(ctx, model: "NeRF", prec: int, rays, z, *params):
         lib = _lib.load()
         dev = rays.device
         n, S = z.shape
         P = n * S
-        img = model.packed_weights("fp32")
+        img = model.packed_weights(prec)
         raw = torch.empty(n, S, 4, device=dev, dtype=torch.float32)
         save_enc = torch.empty(P, 64, device=dev, dtype=torch.float32)
         save_dir = torch.empty(P, 32, device=dev, dtype=torch.float32)
-        save_h = torch.empty(9, P, 256, device=dev, dtype=torch.float32)
+        save_h = torch.empty(8, P, 256, device=dev, dtype=torch.float32)
         save_g = torch.empty(P, 128, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
-            _lib.check(lib.snb_field_forward_train(_lib.ptr(img), _lib.ptr(rays), _lib.ptr(z), n, S, _lib.ptr(raw),
+            _lib.check(lib.snb_field_forward_train(_lib.ptr(img), prec, _lib.ptr(rays), _lib.ptr(z), n, S, _lib.ptr(raw),
                                                    _lib.ptr(save_enc), _lib.ptr(save_dir), _lib.ptr(save_h),
                                                    _lib.ptr(save_g), _lib.stream_ptr(dev)), "snb_field_forward_train")
         ctx.save_for_backward(raw, save_enc, save_dir, save_h, save_g, *params)
@@ -77,14 +77,15 @@ class _FieldPass(torch.autograd.Function):
         ws_a = torch.empty(P, 256, device=dev, dtype=torch.float32)
         ws_b = torch.empty(P, 256, device=dev, dtype=torch.float32)
         ws_s = torch.empty(P, 128, device=dev, dtype=torch.float32)
+        ws_w = torch.empty(_lib.BWD_WS_FLOATS, device=dev, dtype=torch.float32)
         parr = (C.c_void_p * 24)(*[p.data_ptr() for p in ps])
         garr = (C.c_void_p * 24)(*[g.data_ptr() for g in grads])
         with torch.cuda.device(dev):
             _lib.check(lib.snb_field_backward(parr, garr, ctx.new_activation, _lib.ptr(g_raw), _lib.ptr(raw),
                                               _lib.ptr(save_enc), _lib.ptr(save_dir), _lib.ptr(save_h),
                                               _lib.ptr(save_g), P, _lib.ptr(ws_a), _lib.ptr(ws_b), _lib.ptr(ws_s),
-                                              _lib.stream_ptr(dev)), "snb_field_backward")
-        return (None, None, None, *grads)
+                                              _lib.ptr(ws_w), _lib.stream_ptr(dev)), "snb_field_backward")
+        return (None, None, None, None, *grads)
 
 
 class _Composite(torch.autograd.Function):
@@ -128,10 +129,11 @@ def _needs_grad(models) -> bool:
 
 
 def _render_rays_train(models, r, S, Ni, use_disp, perturb, noise_std, white_back, detach_coarse, rng_draw,
-                       return_intermediates=False):
+                       return_intermediates=False, prec: int = 0):
     """render_rays with autograd (reference models/rendering.py:126-335 under grad mode): same
-    kernels for sampling / importance sampling, the fp32 field pass that keeps activations, and
-    the closed-form compositing backward.  Gradients reach the NeRF parameters only."""
+    kernels for sampling / importance sampling, the field pass that keeps activations (in the
+    arithmetic of `prec`: tensor-core modes or the fp32 FFMA kernel), the closed-form compositing
+    backward and the tensor-core / FFMA MLP backward.  Gradients reach the NeRF parameters only."""
     lib = _lib.load()
     dev = r.device
     n = r.shape[0]
@@ -149,7 +151,7 @@ def _render_rays_train(models, r, S, Ni, use_disp, perturb, noise_std, white_bac
                                          n, S, _lib.ptr(z_c), st), "snb_sample_coarse")
 
     def field_pass(model, z, noise):
-        raw = _FieldPass.apply(model, r, z, *model._param_list())
+        raw = _FieldPass.apply(model, prec, r, z, *model._param_list())
         return _Composite.apply(raw, z, r, noise if noise_std != 0 else None, noise_std, white_back)
 
     if detach_coarse:
@@ -282,7 +284,7 @@ def render_rays(models,
             raise NotImplementedError("render_rays(test_time=True) under autograd is not built (the reference "
                                       "never trains with it: models/sinnerf.py:176-186)")
         return _render_rays_train(models, r, S, Ni, bool(use_disp), perturb, noise_std, bool(white_back),
-                                  bool(detach_coarse), rnd, _return_intermediates)
+                                  bool(detach_coarse), rnd, _return_intermediates, prec)
 
     # random draws in the reference's order (rendering.py:281, :224, :43, :224)
     perturb_u = rnd("perturb_u", torch.rand, n, S) if perturb > 0 else None
