@@ -339,9 +339,15 @@ static int run_wgrad(const float* dY, int N, const float* X, int ldx, int K, flo
   return check_launch("wgrad_kernel");
 }
 
+// dgrad_tc.cu: the same product on tensor cores (CTA pairs, W^T resident in shared memory)
+int run_dgrad_tc(const float* dY, int N, const float* W, int ldw, int col_off, const float* mask, const float* extra,
+                 int extra_stride, const float* evec, float* dX, long long P, cudaStream_t st);
+
 static int run_dgrad(const float* dY, int N, const float* W, int ldw, int col_off, const float* mask,
                      const float* extra, int extra_stride, const float* evec, float* dX, long long P,
                      cudaStream_t st) {
+  static const bool simt = getenv("SNB_BWD_SIMT") && atoi(getenv("SNB_BWD_SIMT")) != 0;
+  if (!simt) return run_dgrad_tc(dY, N, W, ldw, col_off, mask, extra, extra_stride, evec, dX, P, st);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DgradSmem));
