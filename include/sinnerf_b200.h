@@ -150,13 +150,13 @@ int snb_composite_backward(const float* raw, const float* z_vals, const float* r
 
 /* Backward of NeRF.forward (autograd through models/nerf.py:105-148) for one field pass.
  * params / grads: HOST arrays of 24 device pointers in state-dict order; grads are ACCUMULATED into
- * (zero them first).  Scratch: ws_a, ws_b (P,256), ws_s (P,128), ws_w (SNB_BWD_WS_FLOATS floats).
- * No gradient reaches rays or z. */
+ * (zero them first).  Scratch: ws_a, ws_b (P,256), ws_s (P,128), ws_w (SNB_BWD_WS_FLOATS floats),
+ * ws_m (P,8) 32-bit words (ReLU masks as bit rows, 16-byte aligned).  No gradient reaches rays or z. */
 #define SNB_BWD_WS_FLOATS (2 * 128 * 256 + 128)
 int snb_field_backward(const float* const* params, float* const* grads, int new_activation,
                        const float* g_raw, const float* raw, const float* save_enc, const float* save_dir,
                        const float* save_h, const float* save_g, int64_t n_points, float* ws_a, float* ws_b,
-                       float* ws_s, float* ws_w, void* stream);
+                       float* ws_s, float* ws_w, uint32_t* ws_m, void* stream);
 
 /* ---- whole path -------------------------------------------------------------------- */
 typedef struct SnbRenderArgs {

@@ -54,7 +54,7 @@ SIGNATURES = {
     "snb_composite_backward": (C.c_int, [c_f, c_f, c_f, c_f, C.c_float, C.c_int, c_f, c_f, c_f, C.c_int64, C.c_int,
                                          c_f, c_f]),
     "snb_field_backward": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, c_f, c_f, c_f, c_f, c_f,
-                                     c_f, C.c_int64, c_f, c_f, c_f, c_f, c_f]),
+                                     c_f, C.c_int64, c_f, c_f, c_f, c_f, c_f, c_f]),
 }
 BWD_WS_FLOATS = 2 * 128 * 256 + 128   # SNB_BWD_WS_FLOATS
 

@@ -44,7 +44,7 @@ int launch_composite_bwd(const float*, const float*, const float*, const float*,
                          const float*, const float*, int64_t, int, float*, cudaStream_t);
 int field_backward_fp32(const float* const*, float* const*, int, const float*, const float*, const float*,
                         const float*, const float*, const float*, int64_t, float*, float*, float*, float*,
-                        cudaStream_t);
+                        uint32_t*, cudaStream_t);
 int launch_generate_rays(const float*, float, float, float, float, float, float, int, int, int, int, int, int, float*,
                          cudaStream_t);
 // tensor-core modes (field_tc.cu)
@@ -225,15 +225,15 @@ int snb_composite_backward(const float* raw, const float* z_vals, const float* r
 int snb_field_backward(const float* const* params, float* const* grads, int new_activation, const float* g_raw,
                        const float* raw, const float* save_enc, const float* save_dir, const float* save_h,
                        const float* save_g, int64_t n_points, float* ws_a, float* ws_b, float* ws_s,
-                       float* ws_w, void* stream) {
+                       float* ws_w, uint32_t* ws_m, void* stream) {
   SNB_REQUIRE(n_points >= 0, "snb_field_backward: negative point count");
   SNB_REQUIRE(params && grads, "snb_field_backward: null parameter arrays");
   for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i)
     SNB_REQUIRE(params[i] && grads[i], "snb_field_backward: parameter / gradient tensor %d is null", i);
-  SNB_REQUIRE(n_points == 0 || (g_raw && raw && save_enc && save_dir && save_h && save_g && ws_a && ws_b && ws_s && ws_w),
+  SNB_REQUIRE(n_points == 0 || (g_raw && raw && save_enc && save_dir && save_h && save_g && ws_a && ws_b && ws_s && ws_w && ws_m),
               "snb_field_backward: null pointer");
   return field_backward_fp32(params, grads, new_activation, g_raw, raw, save_enc, save_dir, save_h, save_g,
-                             n_points, ws_a, ws_b, ws_s, ws_w, reinterpret_cast<cudaStream_t>(stream));
+                             n_points, ws_a, ws_b, ws_s, ws_w, ws_m, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int snb_render_forward(const SnbRenderArgs* a, void* stream) {

@@ -3,8 +3,9 @@
 //   dX[p][k] = ( sum_n dY[p][n] W[n][col_off + k]  +  extra[p] evec[k] ) * [mask[p][k] > 0]        k < 256
 //
 // (reference: autograd through models/nerf.py:105-148; the SIMT version is dgrad_kernel in
-// field_bwd.cu.)  dY (P, N) with N = 256 or 128, mask = the saved post-ReLU input of the layer,
-// extra/evec = the sigma head's rank-1 term at h8.  All tensors are plain row-major fp32.
+// field_bwd.cu.)  dY (P, N) with N = 256 or 128, mask = sign bits of the saved post-ReLU input of
+// the layer (32 B per point, emitted by the wgrad kernel that reads that input anyway), extra/evec =
+// the sigma head's rank-1 term at h8.  dY and dX are plain row-major fp32.
 //
 // Mapping (the forward field kernel's, with HBM as the producer of A):
 //   * a CTA pair owns 256 points; tcgen05.mma.cta_group::2, M = 256, N = 128 per instruction, so the
@@ -13,15 +14,14 @@
 //   * W^T (bf16 hi + lo, K-major canonical layout) is converted ONCE per CTA and stays resident
 //     in shared memory (128 KB: each CTA of the pair holds 64 of a half's 128 rows) -- no weight
 //     streaming at all;
-//   * the A operand lives in TMEM as bf16 hi | lo planes; four converter warps (one per lane
-//     quadrant) read their point's dY row from HBM 64 columns (one K quarter) at a time, split and
-//     tcgen05.st it.  Quarters form a ring with the MMA issuer: quarter q of the next tile is
+//   * the A operand lives in TMEM as bf16 hi | lo planes; eight converter warps (two per lane
+//     quadrant) read their point's dY row from HBM 32 columns at a time, split and tcgen05.st it.  Quarters form a ring with the MMA issuer: quarter q of the next tile is
 //     refilled as soon as this tile's half b has consumed it, so HBM loads stay in flight while
 //     the tensor pipe works;
 //   * bf16 3-product split (hi*hi + lo*hi + hi*lo), fp32 accumulate: gradients need fp32's range.
 //
-// HBM per point and layer: dY 4N + mask 1 KB in, dX 1 KB out (3 KB at N = 256): the kernel is
-// HBM-bound (~0.46 us per 256-point tile at 6.5 TB/s vs 6144 tensor cycles); see DESIGN.md.
+// HBM per point and layer: dY 4N + 32 B of mask in, dX 1 KB out (2 KB at N = 256): the kernel is
+// HBM-bound (~0.08 us per 256-point tile at 6.5 TB/s against 6144 tensor cycles); see DESIGN.md.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -33,7 +33,7 @@ using namespace umma;
 namespace {
 
 constexpr int kDgTile = 128;                 // points per CTA (MMA M = 256 across the pair)
-constexpr int kDgConvWarps = 4, kDgEpiWarps = 4;
+constexpr int kDgConvWarps = 8, kDgEpiWarps = 4;      // converters: two warps per TMEM lane quadrant
 constexpr int kDgMmaWarp = kDgConvWarps + kDgEpiWarps;
 constexpr int kDgThreads = (kDgMmaWarp + 1) * 32;
 constexpr uint32_t kDgColD = 0, kDgColAhi = 256, kDgColAlo = 384;
@@ -41,7 +41,7 @@ constexpr uint32_t kDgColD = 0, kDgColAhi = 256, kDgColAlo = 384;
 struct DgradTcArgs {
   const float* dY;                 // (P, NRED)
   const float* W; int ldw; int col_off;   // nn.Linear weight (NRED, ldw); inputs [col_off, col_off + 256)
-  const float* mask;               // (P,256) nullable
+  const uint32_t* mask_bits;       // (P,8) nullable: bit c of word w = [input[p][32 w + c] > 0] (wgrad_tc emits it)
   const float* extra; int extra_stride;   // nullable per-point scalar
   const float* evec;               // (256), with extra
   float* dX;                       // (P,256)
@@ -146,29 +146,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
     __syncwarp();
   } else if (warp < kDgConvWarps) {
     // ======================= converters: dY rows (HBM) -> bf16 hi | lo planes of A (TMEM) ========
-    const int row = warp * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    for (long long slot = 0; slot < n_slots; ++slot) {
+    // A unit = 32 columns of one point row (128 B).  The two warps of a quadrant take the two
+    // halves of every K quarter; the next unit's loads are issued before the current one is split
+    // and stored, so every thread keeps 128-256 B in flight (HBM latency ~1.3k cycles).
+    const int quad = warp & 3, sub = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const long long n_units = n_slots * kQ;
+    auto load_unit = [&](long long u, float4 (&v)[8]) {
+      const long long slot = u / kQ;
+      const int q = (int)(u - slot * kQ);
       const long long pt = tile_of(slot) * kDgTile + row;
-      const bool live = pt < a.P;
-      const float4* src = reinterpret_cast<const float4*>(a.dY + (live ? pt : 0) * NRED);
-#pragma unroll 1
-      for (int q = 0; q < kQ; ++q) {
-        float4 v[16];
+      if (u < n_units && pt < a.P) {
+        const float4* src = reinterpret_cast<const float4*>(a.dY + pt * NRED + q * 64 + sub * 32);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = live ? __ldg(src + q * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t hi[32], lo[32];
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j);
+      } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          bf16_split_pair(v[j].x, v[j].y, hi[2 * j], lo[2 * j]);
-          bf16_split_pair(v[j].z, v[j].w, hi[2 * j + 1], lo[2 * j + 1]);
-        }
-        if (slot > 0) { mbar_wait(&s.q_free[q], (uint32_t)(slot - 1) & 1); tc_fence_after(); }
-        tmem_st32(tbase + lane_base + kDgColAhi + q * 32, hi);
-        tmem_st32(tbase + lane_base + kDgColAlo + q * 32, lo);
-        tmem_wait_st();
-        tc_fence_before();
-        signal(&s.q_ready[q]);
+        for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store_unit = [&](long long u, const float4 (&v)[8]) {
+      const long long slot = u / kQ;
+      const int q = (int)(u - slot * kQ);
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bf16_split_pair(v[j].x, v[j].y, hi[2 * j], lo[2 * j]);
+        bf16_split_pair(v[j].z, v[j].w, hi[2 * j + 1], lo[2 * j + 1]);
+      }
+      if (slot > 0) { mbar_wait(&s.q_free[q], (uint32_t)(slot - 1) & 1); tc_fence_after(); }
+      tmem_st16(tbase + lane_base + kDgColAhi + q * 32 + sub * 16, hi);
+      tmem_st16(tbase + lane_base + kDgColAlo + q * 32 + sub * 16, lo);
+      tmem_wait_st();
+      tc_fence_before();
+      signal(&s.q_ready[q]);
+    };
+    {
+      float4 x[8], y[8];
+      load_unit(0, x);
+      for (long long u = 0; u < n_units; u += 2) {
+        load_unit(u + 1, y);
+        store_unit(u, x);
+        load_unit(u + 2, x);
+        if (u + 1 < n_units) store_unit(u + 1, y);
       }
     }
   } else {
@@ -180,18 +201,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
       const long long pt = tile_of(slot) * kDgTile + row;
       const bool live = pt < a.P;
       const float ex = (live && a.extra != nullptr) ? a.extra[pt * a.extra_stride] : 0.f;
-      const float4* mrow = reinterpret_cast<const float4*>(a.mask + (live ? pt : 0) * 256);
       float4* orow = reinterpret_cast<float4*>(a.dX + (live ? pt : 0) * 256);
-      const bool masked = a.mask != nullptr;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
-        float4 m[8];
-        auto load_mask = [&](int g) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            m[j] = (live && masked) ? __ldg(mrow + (h * 128 + g * 32) / 4 + j) : make_float4(1.f, 1.f, 1.f, 1.f);
-        };
-        load_mask(0);
+        uint4 mb = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (live && a.mask_bits != nullptr) mb = __ldg(reinterpret_cast<const uint4*>(a.mask_bits + pt * 8) + h);
+        const uint32_t mw[4] = {mb.x, mb.y, mb.z, mb.w};
         mbar_wait(&s.d_full[h], (uint32_t)slot & 1);
         tc_fence_after();
 #pragma unroll
@@ -201,19 +216,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
           tmem_ld32(tbase + lane_base + kDgColD + c0, v);
           tmem_wait_ld();
           if (g == 3) { tc_fence_before(); signal(&s.d_drained[h]); }   // half h is in registers
-          float4 o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 e = *reinterpret_cast<const float4*>(s.evec + c0 + 4 * j);
-            o[j].x = m[j].x > 0.f ? fmaf(ex, e.x, __uint_as_float(v[4 * j])) : 0.f;
-            o[j].y = m[j].y > 0.f ? fmaf(ex, e.y, __uint_as_float(v[4 * j + 1])) : 0.f;
-            o[j].z = m[j].z > 0.f ? fmaf(ex, e.z, __uint_as_float(v[4 * j + 2])) : 0.f;
-            o[j].w = m[j].w > 0.f ? fmaf(ex, e.w, __uint_as_float(v[4 * j + 3])) : 0.f;
-          }
-          if (g < 3) load_mask(g + 1);
-          if (live) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) orow[c0 / 4 + j] = o[j];
+            float4 o;
+            o.x = (mw[g] >> (4 * j)) & 1u ? fmaf(ex, e.x, __uint_as_float(v[4 * j])) : 0.f;
+            o.y = (mw[g] >> (4 * j + 1)) & 1u ? fmaf(ex, e.y, __uint_as_float(v[4 * j + 1])) : 0.f;
+            o.z = (mw[g] >> (4 * j + 2)) & 1u ? fmaf(ex, e.z, __uint_as_float(v[4 * j + 2])) : 0.f;
+            o.w = (mw[g] >> (4 * j + 3)) & 1u ? fmaf(ex, e.w, __uint_as_float(v[4 * j + 3])) : 0.f;
+            if (live) orow[c0 / 4 + j] = o;
           }
         }
       }
@@ -246,11 +257,11 @@ int launch_dgrad_tc(const DgradTcArgs& a, cudaStream_t st) {
 
 }  // namespace
 
-// drop-in for run_dgrad (field_bwd.cu)
-int run_dgrad_tc(const float* dY, int N, const float* W, int ldw, int col_off, const float* mask, const float* extra,
-                 int extra_stride, const float* evec, float* dX, long long P, cudaStream_t st) {
+// run_dgrad (field_bwd.cu) on tensor cores; the ReLU mask arrives as the bit matrix run_wgrad_tc emitted
+int run_dgrad_tc(const float* dY, int N, const float* W, int ldw, int col_off, const uint32_t* mask_bits,
+                 const float* extra, int extra_stride, const float* evec, float* dX, long long P, cudaStream_t st) {
   if (P == 0) return SNB_OK;
-  DgradTcArgs a{dY, W, ldw, col_off, mask, extra, extra_stride, evec, dX, P};
+  DgradTcArgs a{dY, W, ldw, col_off, mask_bits, extra, extra_stride, evec, dX, P};
   if (N == 256) return launch_dgrad_tc<256>(a, st);
   if (N == 128) return launch_dgrad_tc<128>(a, st);
   return fail(SNB_ERR_INVALID, "run_dgrad_tc: unsupported reduction length %d", N);

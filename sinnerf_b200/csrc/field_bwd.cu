@@ -320,13 +320,18 @@ static int dev_sms() {
 
 // wgrad_tc.cu: the same contraction on tensor cores (bf16 hi/lo split, fp32 accumulate in TMEM)
 int run_wgrad_tc(const float* dY, int N, const float* X, int ldx, int K, float* dW, int ldw, int col_off, float* db,
-                 long long P, cudaStream_t st);
+                 uint32_t* x_pos_bits, long long P, cudaStream_t st);
 
-static int run_wgrad(const float* dY, int N, const float* X, int ldx, int K, float* dW, int ldw, int col_off,
-                     float* db, long long P, cudaStream_t st) {
-  // SNB_BWD_SIMT=1 keeps the FFMA kernels (debugging / A-B timing); the tensor-core kernel is the default
+// SNB_BWD_SIMT=1 keeps the FFMA kernels (debugging / A-B timing); the tensor-core kernels are the default
+static bool bwd_simt() {
   static const bool simt = getenv("SNB_BWD_SIMT") && atoi(getenv("SNB_BWD_SIMT")) != 0;
-  if (!simt) return run_wgrad_tc(dY, N, X, ldx, K, dW, ldw, col_off, db, P, st);
+  return simt;
+}
+
+// x_bits (nullable): where the tensor-core kernel leaves [X > 0] for the dgrad of the same layer
+static int run_wgrad(const float* dY, int N, const float* X, int ldx, int K, float* dW, int ldw, int col_off,
+                     float* db, uint32_t* x_bits, long long P, cudaStream_t st) {
+  if (!bwd_simt()) return run_wgrad_tc(dY, N, X, ldx, K, dW, ldw, col_off, db, x_bits, P, st);
   WgradArgs a{dY, N, X, ldx, K, dW, ldw, col_off, db, P, 0};
   const int nb = N / 128, kb = (K + 127) / 128;
   int splits = (2 * dev_sms()) / (nb * kb);
@@ -340,14 +345,14 @@ static int run_wgrad(const float* dY, int N, const float* X, int ldx, int K, flo
 }
 
 // dgrad_tc.cu: the same product on tensor cores (CTA pairs, W^T resident in shared memory)
-int run_dgrad_tc(const float* dY, int N, const float* W, int ldw, int col_off, const float* mask, const float* extra,
-                 int extra_stride, const float* evec, float* dX, long long P, cudaStream_t st);
+int run_dgrad_tc(const float* dY, int N, const float* W, int ldw, int col_off, const uint32_t* mask_bits,
+                 const float* extra, int extra_stride, const float* evec, float* dX, long long P, cudaStream_t st);
 
+// mask: the saved fp32 input of the layer (FFMA kernel); mask_bits: its sign bits (tensor-core kernel)
 static int run_dgrad(const float* dY, int N, const float* W, int ldw, int col_off, const float* mask,
-                     const float* extra, int extra_stride, const float* evec, float* dX, long long P,
-                     cudaStream_t st) {
-  static const bool simt = getenv("SNB_BWD_SIMT") && atoi(getenv("SNB_BWD_SIMT")) != 0;
-  if (!simt) return run_dgrad_tc(dY, N, W, ldw, col_off, mask, extra, extra_stride, evec, dX, P, st);
+                     const uint32_t* mask_bits, const float* extra, int extra_stride, const float* evec, float* dX,
+                     long long P, cudaStream_t st) {
+  if (!bwd_simt()) return run_dgrad_tc(dY, N, W, ldw, col_off, mask_bits, extra, extra_stride, evec, dX, P, st);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DgradSmem));
@@ -416,7 +421,7 @@ __global__ void unfold_grads_kernel(const float* __restrict__ Wd, const float* _
 int field_backward_fp32(const float* const* params, float* const* grads, int new_activation, const float* g_raw,
                         const float* raw, const float* save_enc, const float* save_dir, const float* save_h,
                         const float* save_g, int64_t n_points, float* ws_a, float* ws_b, float* ws_s, float* ws_w,
-                        cudaStream_t st) {
+                        uint32_t* ws_m, cudaStream_t st) {
   const long long P = n_points;
   if (P == 0) return SNB_OK;
   auto H = [&](int l) { return save_h + (size_t)l * P * kWidth; };   // l = 0..7: h1..h8
@@ -432,30 +437,30 @@ int field_backward_fp32(const float* const* params, float* const* grads, int new
   // direction layer with the bottleneck folded in: X = [h8 (through W') | dir]
   fold_weights_kernel<<<128, 256, 0, st>>>(params[18], params[16], ws_w);
   if ((rc = check_launch("fold_weights_kernel"))) return rc;
-  if ((rc = run_wgrad(ws_s, 128, H(7), 256, 256, ws_w + kFoldDW, 256, 0, ws_w + kFoldDB, P, st))) return rc;
-  if ((rc = run_wgrad(ws_s, 128, save_dir, kDirPad, kDirCh, grads[18], 283, 256, nullptr, P, st))) return rc;
+  if ((rc = run_wgrad(ws_s, 128, H(7), 256, 256, ws_w + kFoldDW, 256, 0, ws_w + kFoldDB, ws_m, P, st))) return rc;
+  if ((rc = run_wgrad(ws_s, 128, save_dir, kDirPad, kDirCh, grads[18], 283, 256, nullptr, nullptr, P, st))) return rc;
   unfold_grads_kernel<<<392, 256, 0, st>>>(params[18], params[16], params[17], ws_w, grads[18], grads[19], grads[16],
                                            grads[17]);
   if ((rc = check_launch("unfold_grads_kernel"))) return rc;
   // into h8: through W', plus the sigma head's term; ReLU mask of h8
-  if ((rc = run_dgrad(ws_s, 128, ws_w + kFoldW, 256, 0, H(7), g_raw + 3, 4, params[kSigmaW], ws_b, P, st))) return rc;
+  if ((rc = run_dgrad(ws_s, 128, ws_w + kFoldW, 256, 0, H(7), ws_m, g_raw + 3, 4, params[kSigmaW], ws_b, P, st))) return rc;
   // trunk layers 8..2 (index l = 7..1): dY lives in cur, dX goes to nxt
   float* cur = ws_b;
   float* nxt = ws_a;
   for (int l = 7; l >= 1; --l) {
     const int ldw = l == 4 ? 319 : 256;
     if (l == 4) {
-      if ((rc = run_wgrad(cur, 256, save_enc, kXyzPad, kXyzCh, grads[2 * l], ldw, 0, grads[2 * l + 1], P, st))) return rc;
-      if ((rc = run_wgrad(cur, 256, H(l - 1), 256, 256, grads[2 * l], ldw, kXyzCh, nullptr, P, st))) return rc;
-      if ((rc = run_dgrad(cur, 256, params[2 * l], ldw, kXyzCh, H(l - 1), nullptr, 0, nullptr, nxt, P, st))) return rc;
+      if ((rc = run_wgrad(cur, 256, save_enc, kXyzPad, kXyzCh, grads[2 * l], ldw, 0, grads[2 * l + 1], nullptr, P, st))) return rc;
+      if ((rc = run_wgrad(cur, 256, H(l - 1), 256, 256, grads[2 * l], ldw, kXyzCh, nullptr, ws_m, P, st))) return rc;
+      if ((rc = run_dgrad(cur, 256, params[2 * l], ldw, kXyzCh, H(l - 1), ws_m, nullptr, 0, nullptr, nxt, P, st))) return rc;
     } else {
-      if ((rc = run_wgrad(cur, 256, H(l - 1), 256, 256, grads[2 * l], ldw, 0, grads[2 * l + 1], P, st))) return rc;
-      if ((rc = run_dgrad(cur, 256, params[2 * l], ldw, 0, H(l - 1), nullptr, 0, nullptr, nxt, P, st))) return rc;
+      if ((rc = run_wgrad(cur, 256, H(l - 1), 256, 256, grads[2 * l], ldw, 0, grads[2 * l + 1], ws_m, P, st))) return rc;
+      if ((rc = run_dgrad(cur, 256, params[2 * l], ldw, 0, H(l - 1), ws_m, nullptr, 0, nullptr, nxt, P, st))) return rc;
     }
     float* t = cur; cur = nxt; nxt = t;
   }
   // layer 1: weights only
-  return run_wgrad(cur, 256, save_enc, kXyzPad, kXyzCh, grads[0], 63, 0, grads[1], P, st);
+  return run_wgrad(cur, 256, save_enc, kXyzPad, kXyzCh, grads[0], 63, 0, grads[1], nullptr, P, st);
 }
 
 }  // namespace snb

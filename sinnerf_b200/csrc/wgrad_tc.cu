@@ -53,6 +53,7 @@ struct WgradTcArgs {
   int K;                             // valid columns of X (<= KP)
   float* dW; int ldw; int col_off;   // dW (N, ldw): the block lands at columns [col_off, col_off + K)
   float* db;                         // nullable
+  uint32_t* x_pos_bits;              // nullable, KP = 256 only: (P, 8) words, bit c of word w = [X[p][32 w + c] > 0]
   long long P;
   long long rows_per_split;          // multiple of kWgPoints
 };
@@ -133,21 +134,36 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(WgradTcArgs a) 
     const int fa = tid & 127;
     float bias_acc = 0.f;
     const int n_batches = 2 * n_stages_total;
+    const float* dy_col = a.dY + n_off + fa;                 // this thread's dY column
+    const size_t ldy = (size_t)a.ldy, ldx = (size_t)a.ldx;
     auto load_batch = [&](int bi, float (&va)[kGa][8], float (&vb)[kGb][8]) {
       const long long p0 = r_begin + (long long)bi * kBatchPts;
+      const bool full = p0 + kBatchPts <= r_end;               // whole batch in range: no per-load bound checks
 #pragma unroll
       for (int i = 0; i < kGa; ++i) {
         const long long p = p0 + ((tid >> 7) + 2 * i) * 8;
+        const float* src = dy_col + (size_t)p * ldy;
+        if (full) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) va[i][r] = (p + r < r_end) ? __ldg(a.dY + (p + r) * a.ldy + n_off + fa) : 0.f;
+          for (int r = 0; r < 8; ++r) va[i][r] = __ldg(src + r * ldy);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) va[i][r] = (p + r < r_end) ? __ldg(src + r * ldy) : 0.f;
+        }
       }
 #pragma unroll
       for (int g = 0; g < kGb; ++g) {
         const int idx = tid + 256 * g, fb = idx % KP, j = idx / KP;
         const long long p = p0 + j * 8;
+        const float* src = a.X + (size_t)p * ldx + fb;
+        const bool col_ok = j < kBatchPts / 8 && fb < a.K;
+        if (full && col_ok) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-          vb[g][r] = (j < kBatchPts / 8 && p + r < r_end && fb < a.K) ? __ldg(a.X + (p + r) * a.ldx + fb) : 0.f;
+          for (int r = 0; r < 8; ++r) vb[g][r] = __ldg(src + r * ldx);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) vb[g][r] = (col_ok && p + r < r_end) ? __ldg(src + r * ldx) : 0.f;
+        }
       }
     };
     auto store_batch = [&](int bi, const float (&va)[kGa][8], const float (&vb)[kGb][8]) {
@@ -171,6 +187,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(WgradTcArgs a) 
         if (j < kBatchPts / 8) {
           const int off = (j0 + j) * (KP * 16) + fb * 16;
           split8_store(vb[g], sb_hi + off, sb_lo + off);
+        }
+        if (KP == 256 && a.x_pos_bits != nullptr && blockIdx.x == 0) {
+          // the ReLU mask the following dgrad needs, as a by-product: lanes hold 32 consecutive features of
+          // the same 8 points, so one ballot per point is that point's mask word
+          const long long p = r_begin + (long long)bi * kBatchPts + j * 8;
+          uint32_t mine = 0;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const uint32_t w = __ballot_sync(0xffffffffu, vb[g][r] > 0.f);
+            if ((tid & 31) == r) mine = w;
+          }
+          if ((tid & 31) < 8 && p + (tid & 31) < r_end) a.x_pos_bits[(p + (tid & 31)) * 8 + (fb >> 5)] = mine;
         }
       }
       if (half == 1) {
@@ -253,12 +281,14 @@ int launch_wgrad_tc(WgradTcArgs a, int N, cudaStream_t st) {
 
 }  // namespace
 
-// drop-in for run_wgrad (field_bwd.cu): same arguments, same accumulate-into semantics
+// run_wgrad (field_bwd.cu) on tensor cores: same accumulate-into semantics; optionally also emits the
+// sign bits of X (the ReLU mask of the layer's input) for the dgrad that follows
 int run_wgrad_tc(const float* dY, int N, const float* X, int ldx, int K, float* dW, int ldw, int col_off, float* db,
-                 long long P, cudaStream_t st) {
+                 uint32_t* x_pos_bits, long long P, cudaStream_t st) {
   if (P == 0) return SNB_OK;
   if (N % 128 != 0 || K > 256) return fail(SNB_ERR_INVALID, "run_wgrad_tc: unsupported shape N=%d K=%d", N, K);
-  WgradTcArgs a{dY, N, X, ldx, K, dW, ldw, col_off, db, P, 0};
+  if (x_pos_bits != nullptr && K != 256) return fail(SNB_ERR_INVALID, "run_wgrad_tc: mask bits need K = 256");
+  WgradTcArgs a{dY, N, X, ldx, K, dW, ldw, col_off, db, x_pos_bits, P, 0};
   if (K > 64) return launch_wgrad_tc<256>(a, N, st);
   if (K > 32) return launch_wgrad_tc<64>(a, N, st);
   return launch_wgrad_tc<32>(a, N, st);

@@ -78,13 +78,15 @@ class _FieldPass(torch.autograd.Function):
         ws_b = torch.empty(P, 256, device=dev, dtype=torch.float32)
         ws_s = torch.empty(P, 128, device=dev, dtype=torch.float32)
         ws_w = torch.empty(_lib.BWD_WS_FLOATS, device=dev, dtype=torch.float32)
+        ws_m = torch.empty(P, 8, device=dev, dtype=torch.int32)
         parr = (C.c_void_p * 24)(*[p.data_ptr() for p in ps])
         garr = (C.c_void_p * 24)(*[g.data_ptr() for g in grads])
         with torch.cuda.device(dev):
             _lib.check(lib.snb_field_backward(parr, garr, ctx.new_activation, _lib.ptr(g_raw), _lib.ptr(raw),
                                               _lib.ptr(save_enc), _lib.ptr(save_dir), _lib.ptr(save_h),
                                               _lib.ptr(save_g), P, _lib.ptr(ws_a), _lib.ptr(ws_b), _lib.ptr(ws_s),
-                                              _lib.ptr(ws_w), _lib.stream_ptr(dev)), "snb_field_backward")
+                                              _lib.ptr(ws_w), _lib.ptr(ws_m), _lib.stream_ptr(dev)),
+                       "snb_field_backward")
         return (None, None, None, None, *grads)
 
 
