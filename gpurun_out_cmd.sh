@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
-for pr in f16x3 bf16x3 bf16; do timeout 120 python tools/time_field.py --precision $pr --iters 5; done > gpurun_out/timing_v12.log 2>&1
-timeout 120 python tools/time_field.py --precision f16x3 --samples 64 --sigma-only --iters 5 >> gpurun_out/timing_v12.log 2>&1
-cat gpurun_out/timing_v12.log
-timeout 120 python tools/trace_field.py f16x3 > gpurun_out/trace_f16x3_v12.log 2>&1
-timeout 200 python tools/time_train.py > gpurun_out/train_v12.log 2>&1; tail -1 gpurun_out/train_v12.log
+timeout 400 python -m pytest tests/test_gpu_backward.py -m gpu -q -x > gpurun_out/pytest_bwd.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_bwd.log; grep -E "Error|error|passed|failed|rc=|assert" gpurun_out/pytest_bwd.log | head -20
+timeout 200 python tools/time_train.py > gpurun_out/train_w2.log 2>&1; tail -1 gpurun_out/train_w2.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train.csv python tools/time_train.py --iters 1 > gpurun_out/ncu_train.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_train.csv > gpurun_out/launches_train_summary.txt; head -9 gpurun_out/launches_train_summary.txt

@@ -97,6 +97,40 @@ def test_render_rays_gradients_match_oracle_autograd(weights, train_noise):
             assert rel_l2(got.cpu(), v.grad) <= 1e-3, (name, k, rel_l2(got.cpu(), v.grad))
 
 
+@pytest.mark.parametrize("n_rays,S,Ni", [(37, 20, 12), (1, 64, 64), (130, 33, 7)])
+def test_gradients_ragged_sizes(n_rays, S, Ni):
+    """Point counts that are not multiples of the kernels' tiles (128 points per CTA in the forward and
+    dgrad, 64-point stages and split-P slices in wgrad): same parity bar as above."""
+    from sinnerf_b200.nerf import NeRF, Embedding
+    from sinnerf_b200.rendering import render_rays
+    rays = t(load_npz("render_llff_room_64p64_train.npz")["rays"])
+    rays = rays[torch.arange(n_rays) % rays.shape[0]]
+    pc, pf = orc.default_init_params(0), orc.default_init_params(1)
+    models = []
+    for p_ in (pc, pf):
+        m = NeRF(use_new_activation=True)
+        m.load_state_dict(p_)
+        models.append(m.to(DEV))
+    out = render_rays(models, [Embedding(3, 10), Embedding(3, 4)], rays.to(DEV), S, False, 0, 0, Ni,
+                      _return_intermediates=True)
+    z_f = out["_inter"]["z_fine"].detach().cpu()
+    oc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    of = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+    ref = orc.render_rays(oc, of, rays, N_samples=S, N_importance=Ni, perturb=0, noise_std=0, z_fine_override=z_f)
+    proj = make_proj(ref, 11)
+    loss_of(ref, proj).backward()
+    loss_of(out, proj).backward()
+    for k in ("rgb_fine", "depth_fine", "opacity_fine", "rgb_coarse", "opacity_coarse"):
+        assert rel_l2(out[k].detach().cpu(), ref[k].detach()) <= 1e-4, k
+    for name, ref_params, model in (("coarse", oc, models[0]), ("fine", of, models[1])):
+        sd = dict(model.named_parameters())
+        for k, v in ref_params.items():
+            if float(v.grad.norm()) == 0.0:
+                assert float(sd[k].grad.norm()) == 0.0, (name, k)
+                continue
+            assert rel_l2(sd[k].grad.cpu(), v.grad) <= 1e-3, (name, k, rel_l2(sd[k].grad.cpu(), v.grad))
+
+
 def test_detach_coarse_and_no_grad_paths():
     from sinnerf_b200.nerf import NeRF, Embedding
     from sinnerf_b200.rendering import render_rays
