@@ -201,6 +201,46 @@ def workload_config(n_gpus, precision):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def train_step_rate(models, emb, dev, precision, n_rays=4096, calls=4, iters=3):
+    """Forward + backward of four 4096-ray render_rays calls (64+64 samples, perturb=1, noise_std=1): the NeRF part
+    of one SinNeRF training step.  Not the headline metric -- reported next to it."""
+    import torch
+    from sinnerf_b200 import rendering, synthetic
+    batches = [synthetic.random_rays("lego", n_rays, seed=100 + i).to(dev) for i in range(calls)]
+    target = torch.rand(n_rays, 3, device=dev)
+    params = [p for m in models for p in m.parameters()]
+
+    def step():
+        for p in params:
+            p.grad = None
+        loss = 0.0
+        for r in batches:
+            out = rendering.render_rays(models, emb, r, N_SAMPLES, False, 1.0, 1.0, N_IMPORTANCE, 32768, True,
+                                        precision=precision)
+            loss = loss + ((out["rgb_coarse"] - target) ** 2).mean() + ((out["rgb_fine"] - target) ** 2).mean() \
+                + 0.1 * out["depth_fine"].mean()
+        loss.backward()
+
+    try:
+        step()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+    finally:
+        for p in params:
+            p.grad = None
+    return {"ms": best, "rays_per_s": n_rays * calls / (best / 1e3),
+            "config": f"{calls} x {n_rays} rays forward + backward, {N_SAMPLES}+{N_IMPORTANCE} samples, perturb=1 noise_std=1 "
+                      f"(BASELINE configs[4] shape, NeRF part), precision {precision}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -323,6 +363,11 @@ def main():
     kern_ms = timed(field_only, max(3, min(args.steps, 10))) / max(3, min(args.steps, 10))
     clocks = sampler.stop() if sampler else None
 
+    # ---- informational: the NeRF part of a training step (BASELINE configs[4] shape), rank 0, N = 1
+    train = None
+    if rank == 0 and world == 1:
+        train = train_step_rate(models, emb, dev, precision)
+
     if rank == 0:
         peaks = load_peaks()
         ms_per_step = total_ms / args.steps
@@ -366,6 +411,8 @@ def main():
                                   + ("executed MMA flops: 3 products (hi*hi + hi*lo + lo*hi) x 0.89 (bottleneck folded into the dir layer)" if precision.endswith("x3")
                                      else "FFMA pipe, not tensor cores" if precision == "fp32" else "single pass")},
         }
+        if train is not None:
+            line["train_step"] = train
         if not args.no_cpu_baseline and world == 1:
             rate, cores, dt = cpu_oracle_rate(rays_cpu, 2048)
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
