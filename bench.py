@@ -41,6 +41,25 @@ METRIC = "rays/sec (64c+64f samples, 8x256 MLP)"
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+# stdout carries exactly ONE line, the JSON record: everything else that libraries write to fd 1 (NCCL's
+# version banner, for one) is sent to stderr for the lifetime of the process.
+_JSON_FD = None
+
+
+def capture_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -189,7 +208,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus, precision):
@@ -250,6 +269,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SINNERF_B200_BENCH_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -418,7 +438,7 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
                                     "sample": f"first 2048 rays of the same frame, one pass ({dt:.1f} s), "
                                               f"oracle/render_oracle.py on torch CPU fp32"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-(for n in 8 48; do for w in seed room; do python tools/grad_error.py $n $w sum; SNB_BWD_SIMT=1 python tools/grad_error.py $n $w sum; done; done; SINNERF_B200_PRECISION=fp32 SNB_BWD_SIMT=1 python tools/grad_error.py 8 seed sum; python tools/grad_error.py 8 seed proj) > gpurun_out/grad_error.log 2>&1
-cat gpurun_out/grad_error.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_r01_2gpu.json 2> gpurun_out/bench_r01_2gpu.err; cut -c1-330 gpurun_out/bench_r01_2gpu.json; tail -2 gpurun_out/bench_r01_2gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_r01_2gpu_ref.json 2> gpurun_out/bench_r01_2gpu_ref.err; cut -c1-200 gpurun_out/bench_r01_2gpu_ref.json
+timeout 300 python -m pytest tests -m gpu -q -x -k "shard or distributed or multi" 2>&1 | tail -2
