@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_r01_2gpu.json 2> gpurun_out/bench_r01_2gpu.err; cut -c1-330 gpurun_out/bench_r01_2gpu.json; tail -2 gpurun_out/bench_r01_2gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_r01_2gpu_ref.json 2> gpurun_out/bench_r01_2gpu_ref.err; cut -c1-200 gpurun_out/bench_r01_2gpu_ref.json
-timeout 300 python -m pytest tests -m gpu -q -x -k "shard or distributed or multi" 2>&1 | tail -2
+timeout 400 python -m pytest tests/test_gpu_backward.py -m gpu -q -x > gpurun_out/pytest_bwd.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_bwd.log; grep -E "Error|error|passed|failed|rc=|assert" gpurun_out/pytest_bwd.log | head -20
+timeout 200 python tools/time_train.py > gpurun_out/train_d2.log 2>&1; tail -1 gpurun_out/train_d2.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train.csv python tools/time_train.py --iters 1 > gpurun_out/ncu_train.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_train.csv > gpurun_out/launches_train_summary.txt; head -9 gpurun_out/launches_train_summary.txt

@@ -54,6 +54,11 @@ struct DgSmem {
   static constexpr int kPlaneBytes = (NRED / 8) * 64 * 16;
   alignas(1024) unsigned char b[2][2][kPlaneBytes];
   alignas(16) float evec[256];
+  // per-warp 32 x 32 transposition tiles (row stride 36 words: conflict-free 128-bit accesses both ways).
+  // HBM is read and written with rows-of-128-bytes per quarter warp (4 lines per instruction); the
+  // thread = point-row view TMEM wants is produced here, not by 32-lines-per-instruction global accesses.
+  alignas(16) float cstage[kDgConvWarps][32][36];
+  alignas(16) float estage[kDgEpiWarps][32][36];
   uint64_t q_ready[4], q_free[4], d_full[2], d_drained[2];
   uint32_t tmem_base;
 };
@@ -150,30 +155,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
     // halves of every K quarter; the next unit's loads are issued before the current one is split
     // and stored, so every thread keeps 128-256 B in flight (HBM latency ~1.3k cycles).
     const int quad = warp & 3, sub = warp >> 2;
-    const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const long long n_units = n_slots * kQ;
+    // lane l of a load/store instruction handles 16 bytes of row (l >> 3) + 4 i, chunk l & 7
+    const int rib0 = lane >> 3, chunk = lane & 7;
     auto load_unit = [&](long long u, float4 (&v)[8]) {
       const long long slot = u / kQ;
       const int q = (int)(u - slot * kQ);
-      const long long pt = tile_of(slot) * kDgTile + row;
-      if (u < n_units && pt < a.P) {
-        const float4* src = reinterpret_cast<const float4*>(a.dY + pt * NRED + q * 64 + sub * 32);
+      const long long pt0 = tile_of(slot) * kDgTile + quad * 32;      // first row of this warp's block
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 8; ++i) {
+        const long long pt = pt0 + rib0 + 4 * i;
+        v[i] = (u < n_units && pt < a.P)
+                   ? __ldg(reinterpret_cast<const float4*>(a.dY + pt * NRED + q * 64 + sub * 32) + chunk)
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     auto store_unit = [&](long long u, const float4 (&v)[8]) {
       const long long slot = u / kQ;
       const int q = (int)(u - slot * kQ);
+      float (*st)[36] = s.cstage[warp];
+      __syncwarp();                                   // the previous unit's row reads are done
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(&st[rib0 + 4 * i][chunk * 4]) = v[i];
+      __syncwarp();
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        bf16_split_pair(v[j].x, v[j].y, hi[2 * j], lo[2 * j]);
-        bf16_split_pair(v[j].z, v[j].w, hi[2 * j + 1], lo[2 * j + 1]);
+        const float4 x = *reinterpret_cast<const float4*>(&st[lane][j * 4]);     // this thread's point row
+        bf16_split_pair(x.x, x.y, hi[2 * j], lo[2 * j]);
+        bf16_split_pair(x.z, x.w, hi[2 * j + 1], lo[2 * j + 1]);
       }
       if (slot > 0) { mbar_wait(&s.q_free[q], (uint32_t)(slot - 1) & 1); tc_fence_after(); }
       tmem_st16(tbase + lane_base + kDgColAhi + q * 32 + sub * 16, hi);
@@ -197,11 +208,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const int rib0 = lane >> 3, chunk = lane & 7;
+    float (*st)[36] = s.estage[warp - kDgConvWarps];
     for (long long slot = 0; slot < n_slots; ++slot) {
-      const long long pt = tile_of(slot) * kDgTile + row;
+      const long long pt0 = tile_of(slot) * kDgTile + quad * 32;
+      const long long pt = pt0 + lane;
       const bool live = pt < a.P;
       const float ex = (live && a.extra != nullptr) ? a.extra[pt * a.extra_stride] : 0.f;
-      float4* orow = reinterpret_cast<float4*>(a.dX + (live ? pt : 0) * 256);
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         uint4 mb = make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -216,6 +229,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
           tmem_ld32(tbase + lane_base + kDgColD + c0, v);
           tmem_wait_ld();
           if (g == 3) { tc_fence_before(); signal(&s.d_drained[h]); }   // half h is in registers
+          __syncwarp();                                   // the previous group's tile has been written out
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 e = *reinterpret_cast<const float4*>(s.evec + c0 + 4 * j);
@@ -224,7 +238,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
             o.y = (mw[g] >> (4 * j + 1)) & 1u ? fmaf(ex, e.y, __uint_as_float(v[4 * j + 1])) : 0.f;
             o.z = (mw[g] >> (4 * j + 2)) & 1u ? fmaf(ex, e.z, __uint_as_float(v[4 * j + 2])) : 0.f;
             o.w = (mw[g] >> (4 * j + 3)) & 1u ? fmaf(ex, e.w, __uint_as_float(v[4 * j + 3])) : 0.f;
-            if (live) orow[c0 / 4 + j] = o;
+            *reinterpret_cast<float4*>(&st[lane][j * 4]) = o;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long pr = pt0 + rib0 + 4 * i;
+            if (pr < a.P)
+              *(reinterpret_cast<float4*>(a.dX + pr * 256 + c0) + chunk) = *reinterpret_cast<const float4*>(&st[rib0 + 4 * i][chunk * 4]);
           }
         }
       }
