@@ -383,11 +383,12 @@ int launch_pack_tc(const float* const* params, int precision, int new_activation
 }
 
 // ------------------------------------------------------------------ shared memory
-template <bool kSplit, int kCg>
+template <bool kSplit, int kCg, bool kTrain = false>
 struct TcSmem {
   static constexpr int kParts = kSplit ? 2 : 1;
   static constexpr uint32_t kStageBytes = Geo<kCg>::kPartBytesMax * kParts;   // this CTA's share of a full chunk
-  static constexpr int kStagesRaw = (160 * 1024) / kStageBytes;              // up to 160 KB of weights in flight
+  // up to 160 KB of weights in flight; the training forward gives 64 KB of that to the store tiles below
+  static constexpr int kStagesRaw = ((kTrain ? 96 : 160) * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
   alignas(1024) unsigned char ring[kStages][kStageBytes];
   alignas(128) unsigned char enc[kParts][kTile * kXyzPad * 2];   // canonical [k8][row][8] hi (, lo)
@@ -395,6 +396,10 @@ struct TcSmem {
   alignas(16) float cst[kConstFloats];
   float sigp[4][kTile];           // sigma head partial sums per 32-column group; [0] ends up holding sigma
   // (the rgb head's partial sums alias dir[0], idle by then: float [4][3][kTile])
+  // training forward: per-warp 32 x 16 transposition tiles (row stride 20 words: conflict-free 128-bit
+  // accesses) so the activations leave as 64 contiguous bytes per 4 lanes instead of 16 bytes per lane
+  // at a 1 KB stride -- 8 lines per store instruction instead of 32
+  alignas(16) float store_tile[kTrain ? kEpiWarps : 1][kTrain ? 32 : 1][20];
   uint64_t full[16], empty[16];
   uint64_t d_full[2], a_ready[4], a_free, enc_ready, dir_ready, d_drained;
   uint32_t tmem_base;
@@ -431,7 +436,7 @@ __device__ __forceinline__ uint32_t canon_off(int row, int k) { return (uint32_t
 template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, bool kTrain = false>
 __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   static_assert(!(kTrain && kEmbedded), "the training forward is the fused (rays, z) entry only");
-  using Smem = TcSmem<kSplit, kCg>;
+  using Smem = TcSmem<kSplit, kCg, kTrain>;
   using G = Geo<kCg>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -637,6 +642,21 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     // hand-off to the MMA issuer, which lives in the leader CTA
     auto signal = [&](uint64_t* bar) { if (kCg == 2 && !leader) mbar_arrive_remote(bar, 0); else mbar_arrive(bar); };
     uint32_t ph_d = 0, ph_free = 0;       // ph_d: bit h = parity of d_full[h]
+    // training forward: 16 consecutive columns of this warp's 32 rows -> global, through the warp's tile.
+    // `x4[k]` = this thread's row, columns [4k, 4k+4); dst_block = address of (first row of the block, first column)
+    auto store_block16 = [&](const float4 (&x4)[4], float* dst_block, long long ld, long long pt_block0) {
+      float (*tile)[20] = s.store_tile[kTrain ? warp : 0];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(&tile[lane][4 * k]) = x4[k];
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (lane >> 2) + 8 * i, c = lane & 3;
+        if (pt_block0 + r < p.n_points)
+          *reinterpret_cast<float4*>(dst_block + r * ld + 4 * c) = *reinterpret_cast<const float4*>(&tile[r][4 * c]);
+      }
+    };
 
     // ---- positional encodings of one tile -> smem (canonical, hi/lo).  Split in pieces so they
     // fit the epilogue warps' idle windows: xyz part 0 (identity + 3 of this thread's 5
@@ -767,7 +787,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
             constexpr bool kRelu = decltype(relu_tag)::value, kSigma = decltype(sigma_tag)::value;
             const float2* b2 = reinterpret_cast<const float2*>(bias + c0);
             const float2* w2 = reinterpret_cast<const float2*>(s.cst + CL.sigma_w + c0);
-            float* save_row = kTrain ? p.save_h + ((size_t)l * p.n_points + pt) * kWidth + c0 : nullptr;
+            const long long pt_block0 = pt - lane;      // first row of this warp's 32-row block
+            float* save_blk = kTrain ? p.save_h + ((size_t)l * p.n_points + pt_block0) * kWidth + c0 : nullptr;
+            float4 keep[4];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               float x[4];
@@ -782,7 +804,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
                   sig_part = fmaf(x[2 * e], ww.x, sig_part); sig_part = fmaf(x[2 * e + 1], ww.y, sig_part);
                 }
               }
-              if (kTrain && pt < p.n_points) *reinterpret_cast<float4*>(save_row + 2 * j) = make_float4(x[0], x[1], x[2], x[3]);
+              if (kTrain) {
+                keep[(j >> 1) & 3] = make_float4(x[0], x[1], x[2], x[3]);
+                if (((j >> 1) & 3) == 3) store_block16(keep, save_blk + (j >> 3) * 16, kWidth, pt_block0);
+              }
               split_pair<kBf16, kSplit, kRelu>(x[0], x[1], v[2 * j], v[2 * j + 1]);
               split_pair<kBf16, kSplit, kRelu>(x[2], x[3], v[2 * j + 2], v[2 * j + 3]);
             }
@@ -845,6 +870,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           const float4* w0 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + c0);
           const float4* w1 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + kHalf + c0);
           const float4* w2 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + 2 * kHalf + c0);
+          float4 keep[4];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bb = b4[j4], r0 = w0[j4], r1 = w1[j4], r2 = w2[j4];
@@ -859,8 +885,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
             }
-            if (kTrain && pt < p.n_points)
-              *reinterpret_cast<float4*>(p.save_g + pt * kHalf + c0 + 4 * j4) = make_float4(x[0], x[1], x[2], x[3]);
+            if (kTrain) {
+              keep[j4 & 3] = make_float4(x[0], x[1], x[2], x[3]);
+              if ((j4 & 3) == 3) store_block16(keep, p.save_g + (pt - lane) * kHalf + c0 + (j4 >> 2) * 16, kHalf, pt - lane);
+            }
             a0 = fmaf(x[0], r0.x, a0); a0 = fmaf(x[1], r0.y, a0); a0 = fmaf(x[2], r0.z, a0); a0 = fmaf(x[3], r0.w, a0);
             a1 = fmaf(x[0], r1.x, a1); a1 = fmaf(x[1], r1.y, a1); a1 = fmaf(x[2], r1.z, a1); a1 = fmaf(x[3], r1.w, a1);
             a2 = fmaf(x[0], r2.x, a2); a2 = fmaf(x[1], r2.y, a2); a2 = fmaf(x[2], r2.z, a2); a2 = fmaf(x[3], r2.w, a2);
@@ -897,7 +925,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, bool kTrain = false>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
   static bool configured = false;
-  const size_t smem = sizeof(TcSmem<kSplit, kCg>) + 1024;
+  const size_t smem = sizeof(TcSmem<kSplit, kCg, kTrain>) + 1024;
   auto kern = field_tc_kernel<kBf16, kSplit, kEmbedded, kCg, kTrain>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
