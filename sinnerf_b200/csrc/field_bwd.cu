@@ -258,40 +258,53 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) wr[c][j] = a.Wr[c * 128 + lane * 4 + j];
   float awr[3][4] = {}, abr[3] = {0.f, 0.f, 0.f}, aws[8] = {}, abs_ = 0.f;
-  for (long long p = warp; p < a.P; p += nwarps) {
-    const float4 g = reinterpret_cast<const float4*>(a.g_raw)[p];
-    const float4 o = reinterpret_cast<const float4*>(a.raw)[p];
-    float gp[3];
-    const float gin[3] = {g.x, g.y, g.z}, out[3] = {o.x, o.y, o.z};
+  // 4 points per warp iteration: all their loads are issued before any is used (the kernel is a pure
+  // HBM stream, 2 KB per point; one point at a time left it latency-bound)
+  constexpr int kU = 4;
+  for (long long pb = warp * kU; pb < a.P; pb += nwarps * kU) {
+    float4 g[kU], o[kU], gv[kU], h0[kU], h1[kU];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (a.new_activation) {
-        // y = 0.5 (1 + 1.002 tanh(x/2))  ->  dy/dx = 0.2505 (1 - tanh^2)
-        const float t = (2.0f * out[c] - 1.0f) * (1.0f / 1.002f);
-        gp[c] = gin[c] * 0.2505f * (1.0f - t * t);
-      } else {
-        gp[c] = gin[c] * out[c] * (1.0f - out[c]);
+    for (int u = 0; u < kU; ++u) {
+      const long long p = pb + u < a.P ? pb + u : a.P - 1;      // tail: re-read the last point, contribute nothing
+      g[u] = reinterpret_cast<const float4*>(a.g_raw)[p];
+      o[u] = reinterpret_cast<const float4*>(a.raw)[p];
+      gv[u] = *reinterpret_cast<const float4*>(a.G + p * 128 + lane * 4);
+      h0[u] = *reinterpret_cast<const float4*>(a.H8 + p * 256 + lane * 8);
+      h1[u] = *reinterpret_cast<const float4*>(a.H8 + p * 256 + lane * 8 + 4);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (pb + u >= a.P) break;
+      const long long p = pb + u;
+      float gp[3];
+      const float gin[3] = {g[u].x, g[u].y, g[u].z}, out[3] = {o[u].x, o[u].y, o[u].z};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (a.new_activation) {
+          // y = 0.5 (1 + 1.002 tanh(x/2))  ->  dy/dx = 0.2505 (1 - tanh^2)
+          const float t = (2.0f * out[c] - 1.0f) * (1.0f / 1.002f);
+          gp[c] = gin[c] * 0.2505f * (1.0f - t * t);
+        } else {
+          gp[c] = gin[c] * out[c] * (1.0f - out[c]);
+        }
       }
+      const float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+      float ds[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float dg = wr[0][j] * gp[0] + wr[1][j] * gp[1] + wr[2][j] * gp[2];
+        // softplus'(s) = sigmoid(s) = 1 - exp(-softplus(s));  ReLU' = [g > 0]
+        const float der = a.new_activation ? (1.0f - expf(-gg[j])) : (gg[j] > 0.f ? 1.0f : 0.f);
+        ds[j] = dg * der;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) awr[c][j] = fmaf(gp[c], gg[j], awr[c][j]);
+      }
+      *reinterpret_cast<float4*>(a.dS + p * 128 + lane * 4) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+      const float hv[8] = {h0[u].x, h0[u].y, h0[u].z, h0[u].w, h1[u].x, h1[u].y, h1[u].z, h1[u].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) aws[j] = fmaf(g[u].w, hv[j], aws[j]);
+      if (lane == 0) { abr[0] += gp[0]; abr[1] += gp[1]; abr[2] += gp[2]; abs_ += g[u].w; }
     }
-    const float4 gv = *reinterpret_cast<const float4*>(a.G + p * 128 + lane * 4);
-    const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
-    float ds[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float dg = wr[0][j] * gp[0] + wr[1][j] * gp[1] + wr[2][j] * gp[2];
-      // softplus'(s) = sigmoid(s) = 1 - exp(-softplus(s));  ReLU' = [g > 0]
-      const float der = a.new_activation ? (1.0f - expf(-gg[j])) : (gg[j] > 0.f ? 1.0f : 0.f);
-      ds[j] = dg * der;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) awr[c][j] = fmaf(gp[c], gg[j], awr[c][j]);
-    }
-    *reinterpret_cast<float4*>(a.dS + p * 128 + lane * 4) = make_float4(ds[0], ds[1], ds[2], ds[3]);
-    const float4 h0 = *reinterpret_cast<const float4*>(a.H8 + p * 256 + lane * 8);
-    const float4 h1 = *reinterpret_cast<const float4*>(a.H8 + p * 256 + lane * 8 + 4);
-    const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) aws[j] = fmaf(g.w, hv[j], aws[j]);
-    if (lane == 0) { abr[0] += gp[0]; abr[1] += gp[1]; abr[2] += gp[2]; abs_ += g.w; }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c)
