@@ -131,6 +131,45 @@ def test_gradients_ragged_sizes(n_rays, S, Ni):
             assert rel_l2(sd[k].grad.cpu(), v.grad) <= 1e-3, (name, k, rel_l2(sd[k].grad.cpu(), v.grad))
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16x3", 2e-3), ("bf16", None)])
+def test_gradients_other_training_precisions(precision, tol):
+    """The training forward runs in any precision mode (`precision=` / SINNERF_B200_PRECISION); the backward is
+    the same tensor-core kernels.  fp32 = FFMA forward; bf16 = the autocast-like single-product mode, whose
+    gradients belong to a visibly different function (trained sigma pre-activations span +-700, and bf16
+    keeps 8 bits of them): they are only checked for being finite and of the right magnitude."""
+    from sinnerf_b200.nerf import NeRF, Embedding
+    from sinnerf_b200.rendering import render_rays
+    case = load_npz("render_llff_room_64p64_train.npz")
+    rays = t(case["rays"])[:48]
+    pc, pf = room_params("coarse"), room_params("fine")
+    models = []
+    for p_ in (pc, pf):
+        m = NeRF(use_new_activation=True)
+        m.load_state_dict(p_)
+        models.append(m.to(DEV))
+    out = render_rays(models, [Embedding(3, 10), Embedding(3, 4)], rays.to(DEV), 64, False, 0, 0, 64,
+                      precision=precision, _return_intermediates=True)
+    z_f = out["_inter"]["z_fine"].detach().cpu()
+    oc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    of = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+    ref = orc.render_rays(oc, of, rays, N_samples=64, N_importance=64, perturb=0, noise_std=0, z_fine_override=z_f)
+    proj = make_proj(ref, 7)
+    loss_of(ref, proj).backward()
+    loss_of(out, proj).backward()
+    for name, ref_params, model in (("coarse", oc, models[0]), ("fine", of, models[1])):
+        sd = dict(model.named_parameters())
+        if tol is None:
+            got = torch.cat([sd[k].grad.flatten().cpu() for k in ref_params])
+            want = torch.cat([v.grad.flatten() for v in ref_params.values()])
+            assert bool(torch.isfinite(got).all()), (precision, name)
+            assert 0.2 <= float(got.norm() / want.norm()) <= 5.0, (precision, name, float(got.norm() / want.norm()))
+            continue
+        for k, v in ref_params.items():
+            if float(v.grad.norm()) == 0.0:
+                continue
+            assert rel_l2(sd[k].grad.cpu(), v.grad) <= tol, (precision, name, k, rel_l2(sd[k].grad.cpu(), v.grad))
+
+
 def test_detach_coarse_and_no_grad_paths():
     from sinnerf_b200.nerf import NeRF, Embedding
     from sinnerf_b200.rendering import render_rays
