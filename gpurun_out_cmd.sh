@@ -1,6 +1,2 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
-for pr in f16x3 bf16; do timeout 120 python tools/time_field.py --precision $pr --iters 5; done > gpurun_out/timing_v12b.log 2>&1
-cat gpurun_out/timing_v12b.log
-timeout 120 python tools/trace_field.py f16x3 > gpurun_out/trace_f16x3_v12b.log 2>&1
-git stash -q 2>/dev/null; true
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/bench_r01_8gpu.json 2> gpurun_out/bench_r01_8gpu.err; cut -c1-330 gpurun_out/bench_r01_8gpu.json; tail -2 gpurun_out/bench_r01_8gpu.err
