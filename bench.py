@@ -229,33 +229,42 @@ def train_step_rate(models, emb, dev, precision, n_rays=4096, calls=4, iters=3):
     target = torch.rand(n_rays, 3, device=dev)
     params = [p for m in models for p in m.parameters()]
 
-    def step():
+    def step(multi):
         for p in params:
             p.grad = None
         loss = 0.0
-        for r in batches:
-            out = rendering.render_rays(models, emb, r, N_SAMPLES, False, 1.0, 1.0, N_IMPORTANCE, 32768, True,
-                                        precision=precision)
+        if multi:
+            outs = rendering.render_rays_multi(models, emb, batches, N_SAMPLES, False, 1.0, 1.0, N_IMPORTANCE, 32768, True,
+                                               precision=precision)
+        else:
+            outs = [rendering.render_rays(models, emb, r, N_SAMPLES, False, 1.0, 1.0, N_IMPORTANCE, 32768, True,
+                                          precision=precision) for r in batches]
+        for out in outs:
             loss = loss + ((out["rgb_coarse"] - target) ** 2).mean() + ((out["rgb_fine"] - target) ** 2).mean() \
                 + 0.1 * out["depth_fine"].mean()
         loss.backward()
 
-    try:
-        step()
+    def best_of(multi):
+        step(multi)
         torch.cuda.synchronize()
         best = None
         for _ in range(iters):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            step()
+            step(multi)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             best = ms if best is None else min(best, ms)
+        return best
+
+    try:
+        best = best_of(False)
+        best_multi = best_of(True)
     finally:
         for p in params:
             p.grad = None
-    return {"ms": best, "rays_per_s": n_rays * calls / (best / 1e3),
+    return {"ms": best, "rays_per_s": n_rays * calls / (best / 1e3), "ms_render_rays_multi": best_multi,
             "config": f"{calls} x {n_rays} rays forward + backward, {N_SAMPLES}+{N_IMPORTANCE} samples, perturb=1 noise_std=1 "
                       f"(BASELINE configs[4] shape, NeRF part), precision {precision}"}
 

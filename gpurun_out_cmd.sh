@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/bench_r01_8gpu.json 2> gpurun_out/bench_r01_8gpu.err; cut -c1-330 gpurun_out/bench_r01_8gpu.json; tail -2 gpurun_out/bench_r01_8gpu.err
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "multi" 2>&1 | tail -2
+timeout 200 python tools/time_train.py > gpurun_out/train_sep.log 2>&1; tail -1 gpurun_out/train_sep.log
+timeout 200 python tools/time_train.py --multi > gpurun_out/train_multi.log 2>&1; tail -1 gpurun_out/train_multi.log

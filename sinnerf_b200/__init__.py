@@ -7,7 +7,7 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
     # torch-dependent modules are imported lazily so `import sinnerf_b200.build` stays light
-    if name in ("render_rays", "sample_pdf", "eval_points"):
+    if name in ("render_rays", "render_rays_multi", "sample_pdf", "eval_points"):
         from . import rendering
         return getattr(rendering, name)
     if name in ("NeRF", "Embedding"):

@@ -19,7 +19,7 @@ from . import _lib
 from . import config
 from .nerf import NeRF
 
-__all__ = ["render_rays", "sample_pdf", "eval_points"]
+__all__ = ["render_rays", "render_rays_multi", "sample_pdf", "eval_points"]
 
 # The reference draws `randn` for the sigma noise even when noise_std == 0
 # (models/rendering.py:224).  Keep the draw (generator state parity) unless disabled.
@@ -246,9 +246,9 @@ def render_rays(models,
     logscale embeddings SinNeRF builds (models/sinnerf.py:131-132) -- the kernels compute them
     on the fly, the modules are only inspected.  `chunk` is accepted and ignored: no (P,256)
     activation ever reaches HBM in inference, so there is nothing to chunk.  Under autograd (grad
-    mode on and a model parameter requiring grad) the call runs the training path: fp32 field
-    pass that keeps activations + hand-written backward kernels; gradients reach the NeRF
-    parameters only, as in the reference.  `noisy_coarse` is ignored exactly
+    mode on and a model parameter requiring grad) the call runs the training path: the field
+    pass that also keeps activations + hand-written tensor-core backward kernels; gradients reach
+    the NeRF parameters only, as in the reference.  `noisy_coarse` is ignored exactly
     as in the reference (:138).  Keyword-only extras: `precision` overrides
     sinnerf_b200.config; `_rng` injects the four random tensors (tests).
     """
@@ -341,3 +341,33 @@ def render_rays(models,
     if _return_intermediates:
         result["_inter"] = {"z_coarse": z_c, "raw_coarse": raw_c, "z_fine": z_f, "raw_fine": raw_f}
     return result
+
+
+def render_rays_multi(models, embeddings, ray_batches, *args, **kwargs):
+    """Several `render_rays` calls with the same models and settings as ONE pass.
+
+    SinNeRF's training step renders four ray sets back to back (reference models/sinnerf.py:304-307:
+    the reference-view patch, an unseen-view patch and two random sets) -- eight field passes and, under
+    autograd, eight backward passes, each with its own launches, weight conversions and split-P
+    reductions.  Rays are independent, so the batches are concatenated, rendered once and the result
+    dict is split again; the values of every ray are those of a separate call except that with
+    `perturb > 0` / `noise_std > 0` the random tensors are drawn once for the concatenation (same
+    distribution, different consumption of the generator than four separate calls).
+    Returns a list of result dicts, one per batch, in order."""
+    batches = [_as_rays(r) for r in ray_batches]
+    if not batches:
+        return []
+    sizes = [int(r.shape[0]) for r in batches]
+    out = render_rays(models, embeddings, torch.cat(batches, 0), *args, **kwargs)
+    per_key = {k: torch.split(v, sizes, 0) for k, v in out.items() if not k.startswith("_")}
+    results = [dict() for _ in sizes]
+    for k, parts in per_key.items():
+        for i, part in enumerate(parts):
+            results[i][k] = part
+    # the reference aliases the fine keys to the coarse tensors when N_importance == 0 (rendering.py:330-333)
+    if out.get("rgb_fine") is out.get("rgb_coarse"):
+        for res in results:
+            for k in ("rgb", "depth", "opacity"):
+                if f"{k}_coarse" in res:
+                    res[f"{k}_fine"] = res[f"{k}_coarse"]
+    return results

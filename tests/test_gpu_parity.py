@@ -326,3 +326,26 @@ def test_rng_stream_matches_reference_order():
             b = render_rays(models, emb, rays, 64, False, 1.0, 1.0, 64, _rng=rng)
         assert torch.equal(a["rgb_fine"], b["rgb_fine"]) and torch.equal(a["opacity_fine"], b["opacity_fine"])
     assert torch.equal(a["rgb_fine"], b["rgb_fine"]) and torch.equal(a["opacity_fine"], b["opacity_fine"])
+
+
+def test_render_rays_multi_equals_separate_calls():
+    """render_rays_multi: one pass over the concatenated batches == separate calls, ray by ray."""
+    from sinnerf_b200.nerf import NeRF, Embedding
+    from sinnerf_b200.rendering import render_rays, render_rays_multi
+    import oracle.render_oracle as orc_
+    models = []
+    for seed in (0, 1):
+        m = NeRF(use_new_activation=True)
+        m.load_state_dict(orc_.default_init_params(seed))
+        models.append(m.to(DEV))
+    emb = [Embedding(3, 10), Embedding(3, 4)]
+    rays = t(load_npz("render_lego_seed0_64p64_wb.npz")["rays"]).to(DEV)
+    batches = [rays[:37], rays[37:40], rays[40:128]]
+    with torch.no_grad():
+        multi = render_rays_multi(models, emb, batches, 64, False, 0, 0, 64, 32768, True)
+        for got, r in zip(multi, batches):
+            want = render_rays(models, emb, r, 64, False, 0, 0, 64, 32768, True)
+            assert set(got) == set(want)
+            for k in want:
+                assert got[k].shape == want[k].shape, k
+                assert torch.equal(got[k], want[k]), k

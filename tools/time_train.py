@@ -14,12 +14,13 @@ import torch  # noqa: E402
 from oracle.render_oracle import default_init_params  # noqa: E402  (seeded weights only)
 from sinnerf_b200 import synthetic  # noqa: E402
 from sinnerf_b200.nerf import NeRF, Embedding  # noqa: E402
-from sinnerf_b200.rendering import render_rays  # noqa: E402
+from sinnerf_b200.rendering import render_rays, render_rays_multi  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=4096)
 ap.add_argument("--calls", type=int, default=4)
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--multi", action="store_true", help="one render_rays_multi call instead of --calls separate ones")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 models = []
@@ -36,8 +37,9 @@ def step():
     for m in models:
         m.zero_grad(set_to_none=True)
     loss = 0.0
-    for r in batches:
-        out = render_rays(models, emb, r, 64, False, 1.0, 1.0, 64, 32768, True)
+    outs = render_rays_multi(models, emb, batches, 64, False, 1.0, 1.0, 64, 32768, True) if args.multi else \
+        [render_rays(models, emb, r, 64, False, 1.0, 1.0, 64, 32768, True) for r in batches]
+    for out in outs:
         loss = loss + ((out["rgb_coarse"] - target) ** 2).mean() + ((out["rgb_fine"] - target) ** 2).mean() \
             + 0.1 * out["depth_fine"].mean()
     loss.backward()
