@@ -73,7 +73,14 @@ class _FieldPass(torch.autograd.Function):
         P = raw.shape[0] * raw.shape[1]
         g_raw = g_raw.contiguous().to(torch.float32)
         ps = [p.detach().contiguous() for p in params]
-        grads = [torch.zeros_like(p) for p in ps]
+        # one zero-filled buffer for all 24 gradient tensors (the kernels accumulate into them); every view
+        # starts on a 16-byte boundary
+        offs, total = [], 0
+        for p in ps:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        grads = [flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, ps)]
         ws_a = torch.empty(P, 256, device=dev, dtype=torch.float32)
         ws_b = torch.empty(P, 256, device=dev, dtype=torch.float32)
         ws_s = torch.empty(P, 128, device=dev, dtype=torch.float32)
