@@ -1,17 +1,21 @@
-// field_bwd.cu -- backward of the field MLP (reference: autograd through models/nerf.py:105-148),
-// fp32 FFMA kernels over the activations the training forward kept (field_simt.cu, save_*).
+// field_bwd.cu -- backward of the field MLP (reference: autograd through models/nerf.py:105-148):
+// the driver that walks the layers, the head kernel, the folded bottleneck, and the fp32 FFMA
+// versions of the two GEMMs.  The GEMMs themselves run on tensor cores (wgrad_tc.cu, dgrad_tc.cu).
 //
 // Per render pass, given g_raw (P,4) = dL/d[r,g,b,sigma] from composite_bwd:
 //   heads     : rgb head + its activation, direction-layer activation, sigma head  (head_bwd_kernel)
-//   per layer : dW_l += dY_l^T X_l, db_l += sum dY_l                                (wgrad_kernel)
-//               dX_l  = dY_l W_l  (x ReLU mask of the saved input, + sigma term)    (dgrad_kernel)
-// walking dir layer -> bottleneck -> layers 8..1.  Nothing flows into rays, z or across
-// sample_pdf (the reference detaches it, models/rendering.py:311-313).
+//   dir layer : W' = Wd[:, :256] Wf (fold_weights_kernel); dW', db' by one wgrad against h8; the chain
+//               rule back to Wd, Wf, bf, bd is three P-independent products (unfold_grads_kernel)
+//   per layer : dW_l += dY_l^T X_l, db_l += sum dY_l          (run_wgrad -> wgrad_tc_kernel | wgrad_kernel)
+//               dX_l  = dY_l W_l  (x ReLU mask of the saved input, + sigma term at h8)
+//                                                              (run_dgrad -> dgrad_tc_kernel | dgrad_kernel)
+// walking dir layer -> layers 8..1.  Nothing flows into rays, z or across sample_pdf (the reference
+// detaches it, models/rendering.py:311-313).
 //
-// Activations are plain (P, C) row-major fp32 tensors, so both GEMMs stream rows with 16-byte
-// cp.async copies; wgrad accumulates a 128x128 block of dW per CTA in registers over a slice of
-// P and finishes with atomics (split-P), dgrad is the forward tiling with W used untransposed.
-// Roofline: FP32 FFMA pipe, 2x the forward FLOPs; HBM ~7 KB/point/layer.
+// Activations are plain (P, C) row-major fp32 tensors.  The FFMA kernels (SNB_BWD_SIMT=1) stream rows
+// with 16-byte cp.async copies; wgrad_kernel accumulates a 128x128 block of dW per CTA in registers
+// over a slice of P and finishes with atomics (split-P), dgrad_kernel is the forward tiling with W
+// used untransposed.  Their roofline is the FP32 FFMA pipe; the tensor-core versions are HBM-bound.
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -14,10 +14,14 @@
 //     D with tcgen05.ld, add bias, apply ReLU, split the fp32 value into a 16-bit hi part and a
 //     16-bit lo part and write both back to TMEM columns [256,384) / [384,512) with tcgen05.st;
 //     the MMAs read A straight from TMEM (".ts" operand form);
-//   * weights stream from L2 through an 8-stage smem ring of 16 KB chunks (per CTA: 64 output
-//     rows x 64 K x {hi,lo}) with cp.async.bulk (1-D TMA) + mbarrier complete_tx; the packed image is laid
+//   * weights stream from L2 through a 5-stage smem ring of 32 KB chunk shares (per CTA: 64 output
+//     rows x 128 K x {hi,lo}) with cp.async.bulk (1-D TMA) + mbarrier complete_tx; the packed image is laid
 //     out in exactly the order the MMA warp consumes it, in the SWIZZLE_NONE K-major canonical
-//     core-matrix layout, so one chunk is one contiguous copy;
+//     core-matrix layout, so one share is one contiguous run of copies;
+//   * one elect.sync-elected lane runs the whole MMA-issuer role over a schedule unrolled at compile
+//     time (35 chunks per tile; every wait, operand offset and commit is an immediate): the tensor
+//     queue is 20+ instructions deep and an MMA costs ~10 issue cycles (probes/umma_issue_probe.cu),
+//     so a lean issuer stays ahead of the pipe; a table-driven loop (~200 instructions per chunk) did not;
 //   * fp32 parity (SNB_PREC_F16X3 / BF16X3): x*w ~= xh*wh + xl*wh + xh*wl, three MMAs per K
 //     step with fp32 accumulation -- 22 (fp16) or 16 (bf16) significand bits per operand;
 //     SNB_PREC_BF16 is the single product;
@@ -34,8 +38,13 @@
 // Epilogue a (reads D_a, writes the next layer's A[k0]) overlaps both b phases -- it only has to
 // hold its stores until (b,k0), the last reader of A[k0], has retired; epilogue b overlaps the
 // next layer's (a,k0).  Measured with the clock64 trace (tools/trace_field.py): an epilogue half
-// costs ~1800 cycles against 1536 per MMA phase, so the older interleaved order stalled ~1000
+// costs ~1400 cycles against 1536 per MMA phase, so the older interleaved order stalled ~1000
 // cycles per layer.
+//
+// kTrain (snb_field_forward_train): the same kernel also writes the embeddings and every layer's
+// post-activation output (fp32, row-major) for the backward; those stores go through per-warp
+// shared-memory transposition tiles so that they leave as 64-byte runs, and the weight ring shrinks
+// to 3 stages to make room.
 //
 // Roofline: tensor pipe.  Executed MMA FLOPs are 3x the algorithmic 1 186 816 FLOP/point in the
 // split modes.  HBM traffic: 4 B/point in (z) + 16 B/point out; weights (2.3 MB per tile pass)
