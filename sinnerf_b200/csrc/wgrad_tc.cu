@@ -244,9 +244,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(WgradTcArgs a) 
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kWgConvWarps * 32) : "memory");
-        for (int e = tid; e < 128 * KP; e += kWgConvWarps * 32) {
-          const int m = e / KP, k = e - m * KP;
-          if (k < a.K) atomicAdd(a.dW + (size_t)(mb * 128 + m) * a.ldw + a.col_off + k, out[m * kLd + k]);
+        if (KP % 4 == 0 && a.K == KP && ((a.ldw | a.col_off) & 3) == 0) {
+          // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 atomic operations
+          for (int e = tid; e < 128 * (KP / 4); e += kWgConvWarps * 32) {
+            const int m = e / (KP / 4), k = (e - m * (KP / 4)) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(out + m * kLd + k);
+            float* dst = a.dW + (size_t)(mb * 128 + m) * a.ldw + a.col_off + k;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                         : "memory");
+          }
+        } else {
+          for (int e = tid; e < 128 * KP; e += kWgConvWarps * 32) {
+            const int m = e / KP, k = e - m * KP;
+            if (k < a.K) atomicAdd(a.dW + (size_t)(mb * 128 + m) * a.ldw + a.col_off + k, out[m * kLd + k]);
+          }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kWgConvWarps * 32) : "memory");
       }
