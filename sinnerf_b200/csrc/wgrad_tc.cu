@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(WgradTcArgs a) 
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kWgConvWarps * 32) : "memory");
-        if (KP % 4 == 0 && a.K == KP && ((a.ldw | a.col_off) & 3) == 0) {
+        if (KP % 4 == 0 && a.K == KP && ((a.ldw | a.col_off) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dW) & 15) == 0) {
           // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 atomic operations
           for (int e = tid; e < 128 * (KP / 4); e += kWgConvWarps * 32) {
             const int m = e / (KP / 4), k = (e - m * (KP / 4)) * 4;
