@@ -170,6 +170,44 @@ def test_gradients_other_training_precisions(precision, tol):
             assert rel_l2(sd[k].grad.cpu(), v.grad) <= tol, (precision, name, k, rel_l2(sd[k].grad.cpu(), v.grad))
 
 
+def test_gradients_are_additive_over_ray_sets_at_training_size():
+    """Size-independent property at the training shape (BASELINE configs[4]: 4096-ray calls, 64+64): the
+    gradient of a sum of per-ray losses over two ray sets rendered as one pass (render_rays_multi) equals the
+    sum of the gradients of two separate calls -- exercises the split-P reductions, tile tails and the
+    forward's activation stores on 0.5 M-point passes, where the CPU oracle is too slow to be the checker."""
+    from sinnerf_b200 import synthetic
+    from sinnerf_b200.nerf import NeRF, Embedding
+    from sinnerf_b200.rendering import render_rays, render_rays_multi
+    models = []
+    for seed in (0, 1):
+        m = NeRF(use_new_activation=True)
+        m.load_state_dict(orc.default_init_params(seed))
+        models.append(m.to(DEV))
+    emb = [Embedding(3, 10), Embedding(3, 4)]
+    sets = [synthetic.random_rays("lego", 4096, seed=11).to(DEV), synthetic.random_rays("lego", 3001, seed=12).to(DEV)]
+    g = torch.Generator(device="cpu").manual_seed(3)
+    tg = [torch.rand(r.shape[0], 3, generator=g).to(DEV) for r in sets]
+
+    def loss_of_out(out, target):
+        return ((out["rgb_fine"] - target) ** 2).sum() + ((out["rgb_coarse"] - target) ** 2).sum() + out["depth_fine"].sum()
+
+    def grads():
+        return [p.grad.detach().clone() for m in models for p in m.parameters()]
+
+    for m in models:
+        m.zero_grad(set_to_none=True)
+    sum(loss_of_out(o, t_) for o, t_ in zip(render_rays_multi(models, emb, sets, 64, False, 0, 0, 64, 32768, True), tg)).backward()
+    fused = grads()
+    for m in models:
+        m.zero_grad(set_to_none=True)
+    for r, t_ in zip(sets, tg):
+        loss_of_out(render_rays(models, emb, r, 64, False, 0, 0, 64, 32768, True), t_).backward()
+    separate = grads()
+    for a, b in zip(fused, separate):
+        assert bool(torch.isfinite(a).all())
+        assert rel_l2(a.cpu(), b.cpu()) <= 1e-4, rel_l2(a.cpu(), b.cpu())
+
+
 def test_detach_coarse_and_no_grad_paths():
     from sinnerf_b200.nerf import NeRF, Embedding
     from sinnerf_b200.rendering import render_rays
