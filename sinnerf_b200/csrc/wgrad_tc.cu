@@ -14,7 +14,7 @@
 // A CTA owns a slice of points and ALL out features, so every byte of dY and X is read from HBM
 // exactly once (2 KB per point for a 256x256 layer):
 //   producer  (1 elected thread)  16 points of dY and of X are two contiguous runs in HBM: two
-//             cp.async.bulk copies per batch into a 3-deep raw fp32 ring (mbarrier complete_tx);
+//             cp.async.bulk copies per batch into a 4-deep raw fp32 ring (mbarrier complete_tx);
 //   converters (8 warps)          a thread owns one feature and 8 consecutive points: 8 conflict-free
 //             LDS from the raw tile, split, one 16-byte row of the K-major (SWIZZLE_NONE) core-matrix
 //             layout for the hi plane and one for the lo plane -- the transpose costs nothing extra;
@@ -41,7 +41,7 @@ constexpr int kWgBatch = 16;             // points per batch = one MMA K step
 constexpr int kWgConvWarps = 8;
 constexpr int kWgMmaWarp = kWgConvWarps, kWgLoadWarp = kWgConvWarps + 1;
 constexpr int kWgThreads = (kWgConvWarps + 2) * 32;
-constexpr int kWgRawStages = 3, kWgPlaneBufs = 2;
+constexpr int kWgRawStages = 4, kWgPlaneBufs = 2;
 
 // KP: in features padded to an MMA N (256 / 64 / 32); NM: 128-row out-feature blocks (N = 128 NM); LDX: X row length
 template <int KP, int NM, int LDX>

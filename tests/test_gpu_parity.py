@@ -294,6 +294,8 @@ def test_edge_cases():
     emb = embeddings()
     out = render_rays(models, emb, torch.zeros(0, 8, device=DEV), 64, False, 0, 0, 64)      # autograd path
     assert out["rgb_fine"].shape == (0, 3) and out["opacity_fine"].shape == (0, 128)
+    (out["rgb_fine"].sum() + out["rgb_coarse"].sum()).backward()                              # empty backward: zeros
+    assert all(p.grad is not None and float(p.grad.abs().sum()) == 0.0 for m in models for p in m.parameters())
     with torch.no_grad():                                                                    # inference path
         out = render_rays(models, emb, torch.zeros(0, 8, device=DEV), 64, False, 0, 0, 64)
     assert out["rgb_fine"].shape == (0, 3) and out["opacity_fine"].shape == (0, 128)
