@@ -934,6 +934,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, bool kTrain = false>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
   static bool configured = false;
+  const long long ntiles = (p.n_points + kTile - 1) / kTile;
+  if (ntiles == 0) return SNB_OK;       // an empty pass is a no-op: no CUDA call at all
   const size_t smem = sizeof(TcSmem<kSplit, kCg, kTrain>) + 1024;
   auto kern = field_tc_kernel<kBf16, kSplit, kEmbedded, kCg, kTrain>;
   if (!configured) {
@@ -941,8 +943,6 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(field_tc): %s", cudaGetErrorString(e));
     configured = true;
   }
-  const long long ntiles = (p.n_points + kTile - 1) / kTile;
-  if (ntiles == 0) return SNB_OK;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

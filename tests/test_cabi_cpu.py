@@ -57,6 +57,16 @@ def test_argument_validation_without_gpu(lib):
     a.n_rays = 0
     a.n_samples = 64
     assert lib.snb_render_forward(C.byref(a), None) == 0     # empty input is a no-op
+    # training entry points: precision / null checks come before any CUDA call; empty passes are no-ops
+    assert lib.snb_field_forward_train(None, 99, None, None, 4, 64, None, None, None, None, None, None) == -1
+    assert b"precision" in lib.snb_last_error()
+    assert lib.snb_field_forward_train(None, 1, None, None, 4, 64, None, None, None, None, None, None) == -1
+    assert b"null pointer" in lib.snb_last_error()
+    assert lib.snb_field_forward_train(None, 1, None, None, 0, 64, None, None, None, None, None, None) == 0
+    nul = (C.c_void_p * 24)()
+    assert lib.snb_field_backward(nul, nul, 1, None, None, None, None, None, None, 0, None, None, None, None, None, None) == -1
+    assert b"is null" in lib.snb_last_error()
+    assert lib.snb_field_backward(None, None, 1, None, None, None, None, None, None, 0, None, None, None, None, None, None) == -1
 
 
 def test_product_path_refuses_cpu_tensors():
