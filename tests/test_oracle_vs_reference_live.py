@@ -95,3 +95,32 @@ def test_sample_pdf_oracle_equals_live_reference(ref, seed):
     diff = (got - want).abs()
     assert float(diff.median()) == 0.0
     assert int((diff > 1e-5).sum()) <= 4
+
+
+def test_autograd_oracle_equals_live_reference(ref):
+    """Gradients of a random projection of all outputs w.r.t. all 48 parameter tensors: reference autograd vs
+    autograd through the oracle (perturb and noise on: the sample_pdf detach and the RNG order both matter)."""
+    rays = synthetic.random_rays("llff", 14, seed=21)
+    pc, pf = orc.default_init_params(31), orc.default_init_params(32)
+    models = ref_models(ref, [pc, pf])
+    for m in models:
+        m.train()
+    emb = [ref["Embedding"](3, 10), ref["Embedding"](3, 4)]
+    torch.manual_seed(77)
+    want = ref["render_rays"](models, emb, rays, 32, False, 1.0, 1.0, 24, 1024, False, test_time=False)
+    g = torch.Generator().manual_seed(5)
+    proj = {k: torch.randn(v.shape, generator=g) for k, v in want.items()}
+    sum((want[k] * proj[k]).sum() for k in want).backward()
+    oc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    of = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+    torch.manual_seed(77)
+    got = orc.render_rays(oc, of, rays, N_samples=32, N_importance=24, perturb=1.0, noise_std=1.0, white_back=False)
+    sum((got[k] * proj[k]).sum() for k in want).backward()
+    for params, model in ((oc, models[0]), (of, models[1])):
+        sd = dict(model.named_parameters())
+        for k, v in params.items():
+            a, b = v.grad, sd[k].grad
+            assert (a is None) == (b is None) or float(a.abs().sum()) == 0.0 or float(b.abs().sum()) == 0.0, k
+            if a is None or b is None:
+                continue
+            assert float((a - b).norm()) <= 2e-4 * max(float(b.norm()), 1e-12), (k, float((a - b).norm() / b.norm()))
