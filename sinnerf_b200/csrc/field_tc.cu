@@ -81,7 +81,10 @@ struct Geo {
 
 enum { SRC_ENC = 0, SRC_HID = 1, SRC_DIR = 2 };
 // WAIT_A0..A3: the previous layer's epilogue has stored output columns [64q, 64q+64) (= this layer's K
-// quarter q) into the A operand; A0 / A2 also mean accumulator half a / b has been drained.
+// quarter q) into the A operand -- and the threads that own those columns have read them out of the
+// accumulator.  An MMA with accumulate = 0 overwrites all 128 columns of its half, so the first chunk on
+// half a waits for A0 AND A1 (both column quarters of D_a drained), not just for the quarter whose data it
+// consumes first; half b's first chunk comes after (a,k1), which has waited for A2 and A3.
 enum { WAIT_NONE = 0, WAIT_ENC = 1, WAIT_DIR = 2, WAIT_A0 = 4, WAIT_A1 = 5, WAIT_A2 = 6, WAIT_A3 = 7 };
 enum { COMMIT_NONE = 0, COMMIT_D0 = 1, COMMIT_D1 = 2, COMMIT_AFREE = 4 };   // bit flags
 
@@ -97,7 +100,7 @@ struct alignas(16) Chunk {
   uint8_t wait_mid;  // WAIT_* before step `mid` (a chunk that spans two K quarters)
   uint8_t mid;       // first step of the second part (== steps when there is no second part)
   uint8_t commit;    // COMMIT_* flags after issuing
-  uint8_t pad;
+  uint8_t wait2;     // second WAIT_* before the first step (a chunk that overwrites accumulator half a)
   uint16_t off;      // K16 steps of all earlier chunks: byte offset in the image = off * step bytes
   uint16_t pad2;
 };
@@ -132,15 +135,23 @@ __host__ __device__ constexpr ChunkTable make_chunk_table() {
           Chunk c{};
           c.layer = l; c.half = half; c.src = src; c.a16 = k0 / 16; c.w16 = (wbase + k0) / 16; c.steps = kc / 16;
           c.first = first; c.mid = c.steps; c.off = off;
-          int w = WAIT_NONE, wm = WAIT_NONE;
-          if (src == SRC_ENC && half == 0) w = (l == 0) ? WAIT_ENC : WAIT_A0;   // skip layer: D_a drained
+          int w = WAIT_NONE, w2 = WAIT_NONE, wm = WAIT_NONE;
+          if (src == SRC_ENC && half == 0) {
+            w = (l == 0) ? WAIT_ENC : WAIT_A0;                 // skip layer: D_a drained = both of its quarters
+            if (l != 0) w2 = WAIT_A1;
+          }
           if (src == SRC_DIR) w = WAIT_DIR;
           if (src == SRC_HID && half == 0) {
-            // half a consumes the K quarters as the previous layer's epilogue delivers them
-            if (k0 % 64 == 0) w = (has_enc && k0 == 0) ? WAIT_NONE : WAIT_A0 + k0 / 64;
-            if (kc > 64) { wm = WAIT_A0 + k0 / 64 + 1; c.mid = (64 - k0 % 64) / 16; }
+            // half a consumes K quarters 2 and 3 as the previous layer's epilogue delivers them; quarters 0
+            // and 1 are both needed before the first (accumulator-overwriting) MMA of the half
+            if (k0 == 0) {
+              if (!has_enc) { w = WAIT_A0; w2 = WAIT_A1; }
+            } else {
+              if (k0 % 64 == 0) w = WAIT_A0 + k0 / 64;
+              if (kc > 64) { wm = WAIT_A0 + k0 / 64 + 1; c.mid = (64 - k0 % 64) / 16; }
+            }
           }
-          c.wait = w; c.wait_mid = wm;
+          c.wait = w; c.wait2 = w2; c.wait_mid = wm;
           const bool last_of_half = (seg == 2) || (seg == 1 && k0 + kc == klen && l != 9) || (seg == 0 && !has_hid && k0 + kc == klen);
           if (last_of_half) c.commit = half == 0 ? COMMIT_D0 : COMMIT_D1;
           // the last reader of A[k 0..127] in this layer: half b's chunk ending at K = 128
@@ -171,18 +182,20 @@ __device__ __forceinline__ const ChunkTable& chunk_table() { return kCg == 2 ? c
 // number of waits on barrier code `code` (WAIT_*) in chunks [0, ci) -- plus chunk ci's own `wait` when
 // the question is about its mid-chunk wait.  a_ready[q] completes once per layer epilogue, 8 per
 // slot, so (prior_waits & 1) is the parity to wait for.
-__host__ __device__ constexpr int prior_waits(const ChunkTable& t, int ci, int code, bool for_mid) {
+// stage: 0 = the chunk's first pre-wait, 1 = its second pre-wait, 2 = its mid-chunk wait
+__host__ __device__ constexpr int prior_waits(const ChunkTable& t, int ci, int code, int stage) {
   int n = 0;
-  for (int i = 0; i < ci; ++i) n += (t.c[i].wait == code) + (t.c[i].wait_mid == code);
-  if (for_mid) n += t.c[ci].wait == code;
+  for (int i = 0; i < ci; ++i) n += (t.c[i].wait == code) + (t.c[i].wait2 == code) + (t.c[i].wait_mid == code);
+  if (stage >= 1) n += t.c[ci].wait == code;
+  if (stage >= 2) n += t.c[ci].wait2 == code;
   return n;
 }
 __host__ __device__ constexpr bool wait_counts_ok(const ChunkTable& t) {
   for (int q = 0; q < 4; ++q) {
-    if (prior_waits(t, t.n_total, WAIT_A0 + q, false) != 8) return false;       // layers 1..7 and the dir layer
-    if (prior_waits(t, t.n_sigma_only, WAIT_A0 + q, false) != 7) return false;  // + the explicit drain of layer 8's
+    if (prior_waits(t, t.n_total, WAIT_A0 + q, 0) != 8) return false;       // layers 1..7 and the dir layer
+    if (prior_waits(t, t.n_sigma_only, WAIT_A0 + q, 0) != 7) return false;  // + the explicit drain of layer 8's
   }
-  return prior_waits(t, t.n_total, WAIT_ENC, false) == 1 && prior_waits(t, t.n_total, WAIT_DIR, false) == 1;
+  return prior_waits(t, t.n_total, WAIT_ENC, 0) == 1 && prior_waits(t, t.n_total, WAIT_DIR, 0) == 1;
 }
 static_assert(wait_counts_ok(h_chunks_cg2), "static wait parities");
 
@@ -273,6 +286,35 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
       const float2 b = __half22float2(h);
       const __half2 l = __floats2half2_rn(x0 - b.x, x1 - b.y);
       lo = *reinterpret_cast<const uint32_t*>(&l);
+    } else {
+      lo = 0;
+    }
+  }
+}
+
+// ReLU + split of two PRE-activation values with no separate max / clamp instructions: the packed converts
+// carry .relu and .satfinite themselves.  hi = relu(x) rounded TOWARD ZERO, so the residual x - hi is >= 0
+// whenever x >= 0 and negative only when x < 0 (hi = 0) -- then lo = rn(relu(residual)) is 0, as it must be.
+// (Truncation leaves a residual of up to one ulp of hi instead of half: hi + lo still carries 21 (fp16) /
+// 15 (bf16) significand bits.)  4 + 2 instructions per pair instead of 8 + 2.
+template <bool kBf16, bool kSplit>
+__device__ __forceinline__ void split_pair_relu(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  if (kBf16) {
+    if (kSplit) asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    if (kSplit) {
+      const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+    } else {
+      lo = 0;
+    }
+  } else {
+    if (kSplit) asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    else asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    if (kSplit) {
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+      const float r0 = x0 - b.x, r1 = x1 - b.y;
+      asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
     } else {
       lo = 0;
     }
@@ -555,13 +597,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           if (CI >= T.n_sigma_only && p.sigma_only) return;
           trace(tr, CI * 4 + 0);
           // a_ready[q] completes 8 times per slot (static_assert below): the parity of each wait is static
-          auto wait_code = [&](auto code_tag, auto mid_tag) {
+          auto wait_code = [&](auto code_tag, auto stage_tag) {
             constexpr int w = decltype(code_tag)::value;
             if (w == WAIT_ENC) mbar_wait(&s.enc_ready, slot_par);
             else if (w == WAIT_DIR) mbar_wait(&s.dir_ready, slot_par);
-            else if (w >= WAIT_A0) mbar_wait(&s.a_ready[w - WAIT_A0], prior_waits(T, CI, w, decltype(mid_tag)::value) & 1);
+            else if (w >= WAIT_A0) mbar_wait(&s.a_ready[w - WAIT_A0], prior_waits(T, CI, w, decltype(stage_tag)::value) & 1);
           };
-          wait_code(std::integral_constant<int, c.wait>{}, std::false_type{});
+          wait_code(std::integral_constant<int, c.wait>{}, std::integral_constant<int, 0>{});
+          wait_code(std::integral_constant<int, c.wait2>{}, std::integral_constant<int, 1>{});
           trace(tr, CI * 4 + 1);
           mbar_wait(&s.full[st], ph_full);
           tc_fence_after();
@@ -618,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           if (do_mma) issue_range(I0{}, IM{});
           trace(tr, 512 + CI * 4 + 0);
           if (c.mid < c.steps) {            // the chunk spans two K quarters: the second arrives later
-            wait_code(std::integral_constant<int, c.wait_mid>{}, std::true_type{});
+            wait_code(std::integral_constant<int, c.wait_mid>{}, std::integral_constant<int, 2>{});
             tc_fence_after();
             if (do_mma) issue_range(IM{}, IS{});
             trace(tr, 512 + CI * 4 + 1);
@@ -635,7 +678,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
         if (p.sigma_only) {
           // layer 8's epilogue arrives on a_ready[0..3] with nobody waiting: consume the phases
 #pragma unroll
-          for (int q = 0; q < 4; ++q) mbar_wait(&s.a_ready[q], prior_waits(T, T.n_sigma_only, WAIT_A0 + q, false) & 1);
+          for (int q = 0; q < 4; ++q) mbar_wait(&s.a_ready[q], prior_waits(T, T.n_sigma_only, WAIT_A0 + q, 0) & 1);
         } else {
           // the next slot's layer 1 overwrites D[0,128): wait until the dir-layer epilogue has read it
           mbar_wait(&s.d_drained, slot_par);
@@ -802,6 +845,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               float x[4];
+              if (kRelu && !kSigma && !kTrain) {
+                // nobody needs the fp32 post-activation value: ReLU and the fp16 range guard ride on the converts
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const float2 bb = b2[j + e];
+                  split_pair_relu<kBf16, kSplit>(__uint_as_float(v[2 * (j + e)]) + bb.x, __uint_as_float(v[2 * (j + e) + 1]) + bb.y,
+                                                 v[2 * (j + e)], v[2 * (j + e) + 1]);
+                }
+                continue;
+              }
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const float2 bb = b2[j + e];
