@@ -220,53 +220,193 @@ def workload_config(n_gpus, precision):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def train_step_rate(models, emb, dev, precision, n_rays=4096, calls=4, iters=3):
-    """Forward + backward of four 4096-ray render_rays calls (64+64 samples, perturb=1, noise_std=1): the NeRF part
-    of one SinNeRF training step.  Not the headline metric -- reported next to it."""
-    import torch
+# ----------------------------------------------------------------------------- other BASELINE configs (extras)
+def _fresh_models(dev, NeRF, default_init_params):
+    models = []
+    for seed in (0, 1):
+        m = NeRF(use_new_activation=True)
+        m.load_state_dict(default_init_params(seed))
+        models.append(m.to(dev))
+    return models
+
+
+def _max_over_ranks(ms, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _timed_steps(fn, iters, flush, sync_all, dev, world):
+    """mean ms per call: each call has its own CUDA-event pair, L2 flushed between calls, max over ranks of the sum."""
+    evs = []
+    sync_all()
+    for _ in range(iters):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    sync_all()
+    return _max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev, world) / iters
+
+
+def bench_configs_2(models, emb, dev, lib, flush, sync_all, peaks):
+    """BASELINE configs[2]: 504x378 LLFF shape, the 63x84 stride-4 ray patch (5 292 rays), 64+64 samples, bf16 MLP
+    operands (fp32 accumulate), one B200.  rays/s of a complete render_rays + the fine-pass field kernel alone."""
+    from sinnerf_b200 import _lib, rendering, synthetic
+    if lib.snb_packed_weights_bytes(_lib.PRECISIONS["bf16"]) == 0:
+        return {"unavailable": "bf16 mode not built"}
+    rays = synthetic.patch_rays("llff", 63, 84, 4, seed=0).to(dev)
+    n = rays.shape[0]
+
+    def step():
+        with torch.no_grad():
+            return rendering.render_rays(models, emb, rays, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False, precision="bf16")
+    for _ in range(3):
+        step()
+    ms = _timed_steps(step, 20, flush, sync_all, dev, 1)
+    with torch.no_grad():
+        inter = rendering.render_rays(models, emb, rays, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False, precision="bf16",
+                                      _return_intermediates=True)["_inter"]
+    z_f, raw_f = inter["z_fine"], inter["raw_fine"]
+    S_f = N_SAMPLES + N_IMPORTANCE
+    pid = _lib.PRECISIONS["bf16"]
+    img = models[1].packed_weights(pid)
+
+    def field_only():
+        _lib.check(lib.snb_field_forward(_lib.ptr(img), pid, _lib.ptr(rays), _lib.ptr(z_f), n, S_f, 0, _lib.ptr(raw_f),
+                                         _lib.stream_ptr(dev)), "snb_field_forward")
+    for _ in range(3):
+        field_only()
+    kms = _timed_steps(field_only, 20, flush, sync_all, dev, 1)
+    tf = FLOP_PER_POINT * n * S_f / (kms / 1e3) / 1e12
+    peak = peaks.get("bf16_tflops") or FALLBACK_PEAKS["bf16_tflops"]       # a ~0.3 ms kernel timed alone: the burst figure
+    return {"workload": "configs[2]: 63x84 stride-4 patch of a 504x378 LLFF-shape frame, 5292 rays, 64+64, bf16 operands / fp32 accumulate",
+            "rays": n, "ms": ms, "rays_per_s": n / (ms / 1e3), "dtype": "bf16",
+            "field_kernel_fine": {"ms": kms, "tflops_algorithmic": tf, "frac_of_bf16_peak": tf / peak, "peak": peak,
+                                  "peak_source": f"MEASURED_PEAKS.json ({peaks['_source']}) bf16_tflops (burst)"}}
+
+
+def bench_configs_3_strong(models, emb, dev, rank, world, precision, flush, sync_all):
+    """BASELINE configs[3]: ONE 640x512 DTU-shape frame (327 680 rays, 64+64) strong-scaled over the ranks: every rank
+    renders its contiguous slab and the pixels are all-gathered (16 B/ray).  The driver forms the speed-up from
+    the per-N values."""
     from sinnerf_b200 import rendering, synthetic
-    batches = [synthetic.random_rays("lego", n_rays, seed=100 + i).to(dev) for i in range(calls)]
-    target = torch.rand(n_rays, 3, device=dev)
-    params = [p for m in models for p in m.parameters()]
+    from sinnerf_b200.distributed import render_rays_sharded
+    rays = synthetic.frame_rays("dtu", seed=0).to(dev)
+    n = rays.shape[0]
 
-    def step(multi):
-        for p in params:
-            p.grad = None
-        loss = 0.0
-        if multi:
-            outs = rendering.render_rays_multi(models, emb, batches, N_SAMPLES, False, 1.0, 1.0, N_IMPORTANCE, 32768, True,
-                                               precision=precision)
-        else:
-            outs = [rendering.render_rays(models, emb, r, N_SAMPLES, False, 1.0, 1.0, N_IMPORTANCE, 32768, True,
-                                          precision=precision) for r in batches]
-        for out in outs:
-            loss = loss + ((out["rgb_coarse"] - target) ** 2).mean() + ((out["rgb_fine"] - target) ** 2).mean() \
-                + 0.1 * out["depth_fine"].mean()
-        loss.backward()
+    def render_fn(r):
+        with torch.no_grad():
+            return rendering.render_rays(models, emb, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, True, precision=precision)
 
-    def best_of(multi):
-        step(multi)
-        torch.cuda.synchronize()
-        best = None
-        for _ in range(iters):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step(multi)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
-            best = ms if best is None else min(best, ms)
-        return best
+    def step():
+        return render_rays_sharded(render_fn, rays)
+    for _ in range(2):
+        step()
+    iters = 5
+    ms = _timed_steps(step, iters, flush, sync_all, dev, world)
+    return {"workload": "configs[3]: 640x512 DTU-shape frame, 327680 rays, 64+64, rays sharded over the ranks + NCCL all-gather "
+                        "of [rgb, depth] (16 B/ray)", "scaling": "strong", "n_gpus": world, "rays_total": n,
+            "rays_per_rank": -(-n // world), "ms": ms, "rays_per_s": n / (ms / 1e3), "precision": precision, "iters": iters}
 
+
+def bench_configs_4_train(dev, rank, local_rank, world, precision, flush, sync_all, NeRF, Embedding, default_init_params):
+    """BASELINE configs[4] (NeRF part): one SinNeRF training step per rank -- the four ray sets of
+    models/sinnerf.py:304-307 (4 x 4096 rays, 64+64, perturb = 1, noise_std = 1) as ONE render_rays_multi pass,
+    SmoothL1-depth / MSE-rgb evaluated inside the compositing kernels (8f-3), backward on tensor cores, DDP gradient
+    all-reduce over NCCL when world > 1, FusedAdam step + weight re-pack (8f-4).  The ViT / discriminator branches are
+    reference Python outside the hot path; their gradient enters as dL/d(rgb) of the two patch ray sets (a fixed
+    linear functional here)."""
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from sinnerf_b200 import rendering, synthetic
+    from sinnerf_b200.optim import FusedAdam
+    n_rays, calls = 4096, 4
+    models = _fresh_models(dev, NeRF, default_init_params)
+    emb = [Embedding(3, 10), Embedding(3, 4)]
+    batches = [synthetic.random_rays("lego", n_rays, seed=1000 * rank + 100 + i).to(dev) for i in range(calls)]
+    g = torch.Generator().manual_seed(rank)
+    trgb = torch.rand(n_rays, 3, generator=g).to(dev)
+    tdep = (torch.rand(n_rays, generator=g) * 4 + 2).to(dev)
+    ext = [(torch.randn(n_rays, 3, generator=g) / n_rays).to(dev) for _ in range(2)]
+    specs = [rendering.RayLosses(trgb, tdep), None, None, rendering.RayLosses(None, tdep)]
+
+    class Step(torch.nn.Module):
+        """stand-in for the LightningModule (models/sinnerf.py): owns both NeRFs, forward = the step's loss"""
+
+        def __init__(self, ms):
+            super().__init__()
+            self.nerf_coarse, self.nerf_fine = ms
+
+        def forward(self):
+            res = rendering.render_rays_multi([self.nerf_coarse, self.nerf_fine], emb, batches, N_SAMPLES, False, 1.0, 1.0,
+                                              N_IMPORTANCE, 32768, True, precision=precision, batch_losses=specs)
+            loss = res[0]["loss_rgb"] + 0.1 * res[0]["loss_depth"]
+            for k, w in zip((1, 2), ext):
+                loss = loss + (res[k]["rgb_fine"] * w).sum() + (res[k]["rgb_coarse"] * w).sum()
+            return loss
+
+    mod = Step(models)
+    net = DDP(mod, device_ids=[local_rank]) if world > 1 else mod
+    opt = FusedAdam(models, lr=5e-4, precision=precision)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        net().backward()
+        opt.step()
+    for _ in range(3):
+        step()
+    torch.cuda.reset_peak_memory_stats(dev)
+    iters = 5
+    ms = _timed_steps(step, iters, flush, sync_all, dev, world)
+    peak_gib = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    flops = 3 * FLOP_PER_POINT * n_rays * calls * POINTS_PER_RAY
+    del net, opt, mod, models
+    return {"workload": f"configs[4] (NeRF part): {calls} x {n_rays} rays per rank, 64+64, perturb=1 noise_std=1, render_rays_multi "
+                        "forward + backward, fused per-ray losses, "
+                        + ("DDP gradient all-reduce (NCCL), " if world > 1 else "") + "FusedAdam step + weight re-pack",
+            "n_gpus": world, "ms_per_step": ms, "rays_per_s": n_rays * calls * world / (ms / 1e3), "precision": precision,
+            "tflops_algorithmic_per_gpu": flops / (ms / 1e3) / 1e12, "peak_mem_gib": peak_gib, "iters": iters,
+            "parallelism": f"ddp{world}" if world > 1 else "single GPU"}
+
+
+def torch_cuda_baseline(rays_dev, default_init_params, n_prefix=8192):
+    """The competitor a SinNeRF user has today (reference eval.py:141-155 on a GPU): the reference algorithm as stock
+    PyTorch ops on this B200 -- oracle/render_oracle.py (the restatement pinned to the reference) on CUDA tensors,
+    fp32 and with allow_tf32.  Informational row; not on any product path."""
+    from oracle import render_oracle as orc
+    dev = rays_dev.device
+    pc = {k: v.to(dev) for k, v in default_init_params(0).items()}
+    pf = {k: v.to(dev) for k, v in default_init_params(1).items()}
+    r = rays_dev[:n_prefix].contiguous()
+    out = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     try:
-        best = best_of(False)
-        best_multi = best_of(True)
+        for tag, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(2):
+                    orc.render_rays(pc, pf, r, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, noise_std=0.0, white_back=True)
+                torch.cuda.synchronize()
+                best = None
+                for _ in range(3):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    orc.render_rays(pc, pf, r, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, noise_std=0.0, white_back=True)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1)
+                    best = ms if best is None else min(best, ms)
+            out[tag] = {"ms": best, "rays_per_s": r.shape[0] / (best / 1e3)}
     finally:
-        for p in params:
-            p.grad = None
-    return {"ms": best, "rays_per_s": n_rays * calls / (best / 1e3), "ms_render_rays_multi": best_multi,
-            "config": f"{calls} x {n_rays} rays forward + backward, {N_SAMPLES}+{N_IMPORTANCE} samples, perturb=1 noise_std=1 "
-                      f"(BASELINE configs[4] shape, NeRF part), precision {precision}"}
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out["sample"] = f"first {r.shape[0]} rays of the same 400x400 frame, 64+64, stock PyTorch CUDA ops (cuBLAS sgemm + ATen elementwise)"
+    return out
 
 
 def main():
@@ -277,6 +417,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SINNERF_B200_BENCH_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2]/[3]/[4] and stock-PyTorch rows")
     args = ap.parse_args()
     capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -290,7 +431,7 @@ def main():
     import torch.distributed as dist
     from sinnerf_b200 import _lib, synthetic
     from sinnerf_b200 import build as _build
-    from sinnerf_b200.distributed import pack_pixels
+    from sinnerf_b200.distributed import pack_pixels, PixelGather
     from sinnerf_b200.nerf import NeRF, Embedding
     from sinnerf_b200 import rendering
     from oracle.render_oracle import default_init_params  # weights only (seeded init), not on the timed path
@@ -321,7 +462,7 @@ def main():
     rays_pinned = rays_cpu.pin_memory()
     rays_dev = rays_cpu.to(dev)
     pix_host = torch.empty(n, 4).pin_memory()
-    gathered = torch.empty(n * world, 4, device=dev) if world > 1 else None
+    gather = PixelGather(n, dev) if world > 1 else None      # gather k overlaps render k + 1 (no per-step barrier)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rendering.DRAW_UNUSED_NOISE = True     # keep the reference's randn draws (rendering.py:224)
 
@@ -331,10 +472,12 @@ def main():
                                         precision=precision)
         pix = pack_pixels(res)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, pix)
+            gather.submit(pix)
         return pix
 
     def sync_all():
+        if gather is not None:
+            gather.wait_all()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -392,10 +535,17 @@ def main():
     kern_ms = timed(field_only, max(3, min(args.steps, 10))) / max(3, min(args.steps, 10))
     clocks = sampler.stop() if sampler else None
 
-    # ---- informational: the NeRF part of a training step (BASELINE configs[4] shape), rank 0, N = 1
-    train = None
-    if rank == 0 and world == 1:
-        train = train_step_rate(models, emb, dev, precision)
+    # ---- the other BASELINE configs, outside the headline timed region (extra keys of the same JSON line)
+    extra = {}
+    if not args.no_extras:
+        peaks_x = load_peaks()
+        if world == 1:
+            extra["configs_2"] = bench_configs_2(models, emb, dev, lib, flush, sync_all, peaks_x)
+        extra["configs_3_strong"] = bench_configs_3_strong(models, emb, dev, rank, world, precision, flush, sync_all)
+        extra["configs_4_ddp"] = bench_configs_4_train(dev, rank, local_rank, world, precision, flush, sync_all, NeRF, Embedding,
+                                                       default_init_params)
+        if world == 1:
+            extra["torch_cuda_baseline"] = torch_cuda_baseline(rays_dev, default_init_params)
 
     if rank == 0:
         peaks = load_peaks()
@@ -427,7 +577,9 @@ def main():
             "config": workload_config(world, precision),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 32 * world,
                     "d2h_bytes_per_step": n * 16 * world, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": 6 * args.steps,
+            # per render_rays: sample_coarse, field, composite, importance_merge, field, composite + per model the
+            # weight-image check kernel and the two (conditional, normally empty) pack kernels
+            "gpu_launches": 12 * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "fine-pass field kernel (160000 rays x 128 samples)",
                          "achieved": kern_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
@@ -440,8 +592,10 @@ def main():
                                   + ("executed MMA flops: 3 products (hi*hi + hi*lo + lo*hi) x 0.89 (bottleneck folded into the dir layer)" if precision.endswith("x3")
                                      else "FFMA pipe, not tensor cores" if precision == "fp32" else "single pass")},
         }
-        if train is not None:
-            line["train_step"] = train
+        line["roofline"]["traffic_source"] = ("static: dram__bytes_read+write of one ncu --set full capture of this kernel at this "
+                                              "size (profiles/field_traffic.json), not re-measured in this run")
+        if extra:
+            line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:
             rate, cores, dt = cpu_oracle_rate(rays_cpu, 2048)
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",

@@ -77,6 +77,15 @@ size_t snb_packed_weights_bytes(int precision);
  *                 0 = ReLU/Sigmoid (models/nerf.py:92-103); stored in the image header. */
 int snb_pack_weights(const float* const* params, int precision, int new_activation, void* packed,
                      void* stream);
+/* Same, but packs only if `packed` does not already hold an image of exactly these parameter VALUES in this
+ * mode: a check kernel recomputes a 64-bit checksum of the 24 tensors on the device and compares it with
+ * the one in the image header; the pack kernels return at once when it matches.  No host synchronisation.
+ * This is what NeRF.packed_weights() calls before every pass: optimizers that update weights through
+ * `p.data` (reference utils/optimizers.py:98,104,180,187,268: RAdam / PlainRAdam / AdamW / Ranger) do not
+ * bump autograd's version counter, so no host-side key can tell that the image is stale.
+ * `packed` must start out zero-filled (or hold an earlier image). */
+int snb_refresh_weights(const float* const* params, int precision, int new_activation, void* packed,
+                        void* stream);
 
 /* ---- stages (each maps to one oracle function) ------------------------------------- */
 
@@ -148,6 +157,39 @@ int snb_composite_backward(const float* raw, const float* z_vals, const float* r
                            float noise_std, int white_back, const float* g_rgb, const float* g_depth,
                            const float* g_weights, int64_t n_rays, int n_samples, float* g_raw, void* stream);
 
+/* ---- per-ray losses folded into the compositing ------------------------------------
+ * The two losses SinNeRF puts directly on render_rays' outputs (models/sinnerf.py:310-319):
+ *   MSELoss  (losses.py:12-22, nn.MSELoss 'mean' on rgb_coarse / rgb_fine)
+ *   SL1Loss  (models/sinnerf.py:32-42, nn.SmoothL1Loss 'mean', beta = 1, on depth_coarse / depth_fine)
+ * as weighted per-ray sums, so several ray sets with their own normalisation can share one pass:
+ *   loss[0] = sum_ray rgb_weight[ray]   * sum_c (rgb[ray][c] - target_rgb[ray][c])^2     (1/(3N): 'mean')
+ *   loss[1] = sum_ray depth_weight[ray] * smooth_l1(depth[ray] - target_depth[ray])       (1/N: 'mean')
+ * A NULL target drops that term; NULL per-ray weights mean the scalar *_weight0 for every ray. */
+typedef struct SnbLossSpec {
+  const float* target_rgb;    /* (N,3) or NULL */
+  const float* target_depth;  /* (N,)  or NULL */
+  const float* rgb_weight;    /* (N,)  or NULL */
+  const float* depth_weight;  /* (N,)  or NULL */
+  float rgb_weight0, depth_weight0;
+} SnbLossSpec;
+/* floats of zero-initialised scratch for the deterministic loss reduction (reusable across calls on one stream) */
+#define SNB_LOSS_WS_FLOATS 4096
+/* snb_composite_forward with raw_channels = 4 that also writes loss (2,) = [loss[0], loss[1]] above. */
+int snb_composite_forward_loss(const float* raw, const float* z_vals, const float* rays, const float* noise,
+                               float noise_std, int white_back, int64_t n_rays, int n_samples,
+                               const SnbLossSpec* loss, float* rgb, float* depth, float* weights, float* loss_out,
+                               float* loss_ws, void* stream);
+/* snb_composite_backward where dL/d(rgb, depth) = the given g_rgb / g_depth (either may be NULL) PLUS the
+ * derivative of g_loss[0] loss[0] + g_loss[1] loss[1] (g_loss: device (2,), NULL = ones; `loss` may be NULL),
+ * formed per ray in registers from the forward's rgb / depth outputs -- no (N,3)/(N,) gradient tensors and
+ * no elementwise loss kernels.  g_amax (nullable): one 32-bit word, atomically raised to the bit pattern of
+ * max |g_raw| (zero it first) -- the scale statistic of the 16-bit field backward. */
+int snb_composite_backward_loss(const float* raw, const float* z_vals, const float* rays, const float* noise,
+                                float noise_std, int white_back, const float* g_rgb, const float* g_depth,
+                                const float* g_weights, const SnbLossSpec* loss, const float* rgb, const float* depth,
+                                const float* g_loss, int64_t n_rays, int n_samples, float* g_raw, float* g_amax,
+                                void* stream);
+
 /* Backward of NeRF.forward (autograd through models/nerf.py:105-148) for one field pass.
  * params / grads: HOST arrays of 24 device pointers in state-dict order; grads are ACCUMULATED into
  * (zero them first).  Scratch: ws_a, ws_b (P,256), ws_s (P,128), ws_w (SNB_BWD_WS_FLOATS floats),
@@ -157,6 +199,23 @@ int snb_field_backward(const float* const* params, float* const* grads, int new_
                        const float* g_raw, const float* raw, const float* save_enc, const float* save_dir,
                        const float* save_h, const float* save_g, int64_t n_points, float* ws_a, float* ws_b,
                        float* ws_s, float* ws_w, uint32_t* ws_m, void* stream);
+
+/* ---- optimiser step --------------------------------------------------------------
+ * torch.optim.Adam as the reference configures it (utils/__init__.py:19-21: lr, eps = 1e-8, weight_decay;
+ * betas default (0.9, 0.999), amsgrad off), fused over the 24 parameter tensors of one NeRF, followed on the
+ * same stream by the re-pack of `packed` (may be NULL: no re-pack) so that the image the field kernels
+ * stream is up to date -- and stamped clean for snb_refresh_weights -- when the call returns.
+ * params: HOST array of 24 device pointers (updated in place); grads: HOST array of 24 device pointers, a
+ * NULL entry = no gradient for that tensor (skipped, as torch does); exp_avg / exp_avg_sq: device buffers
+ * of SNB_PARAM_FLOATS floats (the tensors' flat concatenation in state-dict order), zero before step 1.
+ * step = 1 for the first update. */
+#define SNB_PARAM_FLOATS 595844
+typedef struct SnbAdamArgs {
+  double lr, beta1, beta2, eps, weight_decay;   /* doubles: torch forms its scalars from python floats */
+  int step;
+} SnbAdamArgs;
+int snb_adam_step(float* const* params, const float* const* grads, float* exp_avg, float* exp_avg_sq,
+                  const SnbAdamArgs* args, int precision, int new_activation, void* packed, void* stream);
 
 /* ---- whole path -------------------------------------------------------------------- */
 typedef struct SnbRenderArgs {

@@ -110,7 +110,7 @@ def sample_z(near: Tensor, far: Tensor, n_samples: int, use_disp: bool = False,
     (rendering.py:264 passes no dtype).  perturb_u is the U[0,1) tensor the
     reference draws at :281; pass it to replay a specific draw.
     """
-    t = torch.linspace(0, 1, n_samples).to(near.dtype)
+    t = torch.linspace(0, 1, n_samples).to(near)       # values formed on the host (as the reference does), then moved
     if not use_disp:
         z = near * (1 - t) + far * t
     else:
@@ -121,7 +121,7 @@ def sample_z(near: Tensor, far: Tensor, n_samples: int, use_disp: bool = False,
         upper = torch.cat([mid, z[:, -1:]], dim=-1)
         lower = torch.cat([z[:, :1], mid], dim=-1)
         if perturb_u is None:
-            perturb_u = torch.rand(z.shape)
+            perturb_u = torch.rand(z.shape, device=z.device)
         z = lower + (upper - lower) * (perturb * perturb_u)
     return z
 
@@ -169,9 +169,9 @@ def sample_pdf(bins: Tensor, weights: Tensor, n_importance: int, det: bool = Fal
     pdf = w / w.sum(dim=-1, keepdim=True)
     cdf = torch.cat([torch.zeros_like(pdf[:, :1]), torch.cumsum(pdf, dim=-1)], dim=-1)
     if det:
-        u = torch.linspace(0, 1, n_importance).to(bins.dtype).expand(n_rays, n_importance)
+        u = torch.linspace(0, 1, n_importance).to(bins).expand(n_rays, n_importance)
     elif u is None:
-        u = torch.rand(n_rays, n_importance).to(bins.dtype)
+        u = torch.rand(n_rays, n_importance, device=bins.device).to(bins.dtype)
     u = u.contiguous()
     idx = torch.searchsorted(cdf, u, right=True)
     lo = (idx - 1).clamp_min(0)
@@ -236,11 +236,11 @@ def render_rays(coarse: Params, fine: Optional[Params], rays: Tensor, N_samples:
     dir_enc = embed(rays_d, N_DIR_FREQS)                       # rendering.py:261
 
     if perturb > 0 and "perturb_u" not in rng:
-        rng["perturb_u"] = torch.rand(n, N_samples)            # RNG call 1 (:281)
+        rng["perturb_u"] = torch.rand(n, N_samples, device=rays.device)            # RNG call 1 (:281)
     z = sample_z(near, far, N_samples, use_disp, perturb, rng.get("perturb_u"))
 
     if "noise_coarse" not in rng:
-        rng["noise_coarse"] = torch.randn(n, N_samples)        # RNG call 2 (:224)
+        rng["noise_coarse"] = torch.randn(n, N_samples, device=rays.device)        # RNG call 2 (:224)
     noise_c = rng["noise_coarse"].to(rays.dtype) * noise_std
     c = field_pass(coarse, rays_o, rays_d, dir_enc, z, noise_c, white_back,
                    weights_only=test_time, new_activation=new_activation)
@@ -253,7 +253,7 @@ def render_rays(coarse: Params, fine: Optional[Params], rays: Tensor, N_samples:
         z_mid = 0.5 * (z[:, :-1] + z[:, 1:])                    # :310
         det = perturb == 0
         if not det and "pdf_u" not in rng:
-            rng["pdf_u"] = torch.rand(n, N_importance)         # RNG call 3 (:43)
+            rng["pdf_u"] = torch.rand(n, N_importance, device=rays.device)         # RNG call 3 (:43)
         z_new = sample_pdf(z_mid, c["weights"][:, 1:-1], N_importance, det=det,
                            u=None if det else rng["pdf_u"].to(rays.dtype)).detach()
         # ^ detach: no gradient flows from the fine pass into the coarse weights (:311-313)
@@ -261,7 +261,7 @@ def render_rays(coarse: Params, fine: Optional[Params], rays: Tensor, N_samples:
         if z_fine_override is not None:
             z_f = z_fine_override
         if "noise_fine" not in rng:
-            rng["noise_fine"] = torch.randn(n, N_samples + N_importance)  # RNG call 4
+            rng["noise_fine"] = torch.randn(n, N_samples + N_importance, device=rays.device)  # RNG call 4
         noise_f = rng["noise_fine"].to(rays.dtype) * noise_std
         f = field_pass(fine, rays_o, rays_d, dir_enc, z_f, noise_f, white_back,
                        new_activation=new_activation)

@@ -31,6 +31,19 @@ class SnbRenderArgs(C.Structure):
     ]
 
 
+class SnbLossSpec(C.Structure):
+    _fields_ = [("target_rgb", c_f), ("target_depth", c_f), ("rgb_weight", c_f), ("depth_weight", c_f),
+                ("rgb_weight0", C.c_float), ("depth_weight0", C.c_float)]
+
+
+class SnbAdamArgs(C.Structure):
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("step", C.c_int)]
+
+
+LOSS_WS_FLOATS = 4096   # SNB_LOSS_WS_FLOATS
+PARAM_FLOATS = 595844   # SNB_PARAM_FLOATS
+
 # name -> (restype, argtypes); must list every symbol include/sinnerf_b200.h declares
 SIGNATURES = {
     "snb_version": (C.c_int, []),
@@ -38,6 +51,7 @@ SIGNATURES = {
     "snb_device_check": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "snb_packed_weights_bytes": (C.c_size_t, [C.c_int]),
     "snb_pack_weights": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, c_f, c_f]),
+    "snb_refresh_weights": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, c_f, c_f]),
     "snb_sample_coarse": (C.c_int, [c_f, c_f, c_f, C.c_float, C.c_int, C.c_int64, C.c_int, c_f, c_f]),
     "snb_embed": (C.c_int, [c_f, C.c_int64, C.c_int, C.c_int, c_f, c_f]),
     "snb_mlp_forward": (C.c_int, [c_f, C.c_int, c_f, C.c_int64, C.c_int64, C.c_int, c_f, c_f]),
@@ -53,6 +67,12 @@ SIGNATURES = {
     "snb_field_forward_train": (C.c_int, [c_f, C.c_int, c_f, c_f, C.c_int64, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f]),
     "snb_composite_backward": (C.c_int, [c_f, c_f, c_f, c_f, C.c_float, C.c_int, c_f, c_f, c_f, C.c_int64, C.c_int,
                                          c_f, c_f]),
+    "snb_composite_forward_loss": (C.c_int, [c_f, c_f, c_f, c_f, C.c_float, C.c_int, C.c_int64, C.c_int,
+                                             C.POINTER(SnbLossSpec), c_f, c_f, c_f, c_f, c_f, c_f]),
+    "snb_composite_backward_loss": (C.c_int, [c_f, c_f, c_f, c_f, C.c_float, C.c_int, c_f, c_f, c_f,
+                                              C.POINTER(SnbLossSpec), c_f, c_f, c_f, C.c_int64, C.c_int, c_f, c_f, c_f]),
+    "snb_adam_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_f, c_f, C.POINTER(SnbAdamArgs),
+                                C.c_int, C.c_int, c_f, c_f]),
     "snb_field_backward": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, c_f, c_f, c_f, c_f, c_f,
                                      c_f, C.c_int64, c_f, c_f, c_f, c_f, c_f, c_f]),
 }

@@ -26,30 +26,45 @@ int check_launch(const char* what) {
   return SNB_OK;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  return dev;
+}
+
+int sm_count() {
+  static int sms[kMaxDevices];
+  const int dev = current_device() & (kMaxDevices - 1);
+  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
+}
+
 // launchers defined in ray_kernels.cu / field_simt.cu / field_tc.cu
 int launch_sample_coarse(const float*, const float*, const float*, float, int, int64_t, int, float*, cudaStream_t);
 int launch_embed(const float*, int64_t, int, int, float*, cudaStream_t);
 int launch_composite(const float*, int, const float*, const float*, const float*, float, int, int64_t, int,
-                     float*, float*, float*, cudaStream_t);
+                     float*, float*, float*, const SnbLossSpec*, float*, float*, cudaStream_t);
 int launch_sample_pdf(const float*, int64_t, const float*, int64_t, const float*, int64_t, int64_t, int, int,
                       float, float*, cudaStream_t);
 int launch_importance_merge(const float*, const float*, const float*, int64_t, int64_t, int, int, float, float*,
                             float*, cudaStream_t);
-int launch_pack_fp32(const float* const*, int, void*, cudaStream_t);
+int launch_pack_fp32(const float* const*, int, void*, int, cudaStream_t);
 int field_forward_fp32(const void*, const float*, const float*, int64_t, int, int, float*, cudaStream_t);
 int mlp_forward_fp32(const void*, const float*, int64_t, int64_t, int, float*, cudaStream_t);
 int field_forward_train_fp32(const void*, const float*, const float*, int64_t, int, float*, float*, float*, float*,
                              float*, cudaStream_t);
 int launch_composite_bwd(const float*, const float*, const float*, const float*, float, int, const float*,
-                         const float*, const float*, int64_t, int, float*, cudaStream_t);
+                         const float*, const float*, int64_t, int, float*, const SnbLossSpec*, const float*,
+                         const float*, const float*, float*, cudaStream_t);
 int field_backward_fp32(const float* const*, float* const*, int, const float*, const float*, const float*,
                         const float*, const float*, const float*, int64_t, float*, float*, float*, float*,
                         uint32_t*, cudaStream_t);
 int launch_generate_rays(const float*, float, float, float, float, float, float, int, int, int, int, int, int, float*,
                          cudaStream_t);
+int adam_step_pack(float* const*, const float* const*, float*, float*, const SnbAdamArgs&, int, int, void*, cudaStream_t);
 // tensor-core modes (field_tc.cu)
 size_t tc_packed_bytes(int precision);
-int launch_pack_tc(const float* const*, int, int, void*, cudaStream_t);
+int launch_pack_tc(const float* const*, int, int, void*, int, cudaStream_t);
 int field_forward_tc(const void*, int, const float*, const float*, int64_t, int, int, float*, cudaStream_t);
 int mlp_forward_tc(const void*, int, const float*, int64_t, int64_t, int, float*, cudaStream_t);
 int field_forward_train_tc(const void*, int, const float*, const float*, int64_t, int, float*, float*, float*, float*,
@@ -96,15 +111,28 @@ size_t snb_packed_weights_bytes(int precision) {
   return 0;
 }
 
-int snb_pack_weights(const float* const* params, int precision, int new_activation, void* packed, void* stream) {
-  SNB_REQUIRE(params != nullptr && packed != nullptr, "snb_pack_weights: null pointer");
-  SNB_REQUIRE(aligned16(packed), "snb_pack_weights: packed image must be 16-byte aligned");
+static int pack_weights_impl(const char* who, const float* const* params, int precision, int new_activation,
+                             void* packed, int only_if_dirty, void* stream) {
+  SNB_REQUIRE(params != nullptr && packed != nullptr, "%s: null pointer", who);
+  SNB_REQUIRE(aligned16(packed), "%s: packed image must be 16-byte aligned", who);
   for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i)
-    SNB_REQUIRE(params[i] != nullptr, "snb_pack_weights: parameter tensor %d is null", i);
+    SNB_REQUIRE(params[i] != nullptr, "%s: parameter tensor %d is null", who, i);
   if (int rc = check_precision(precision)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (precision == SNB_PREC_FP32) return launch_pack_fp32(params, new_activation, packed, st);
-  return launch_pack_tc(params, precision, new_activation, packed, st);
+  // the check kernel always runs: it also stamps the header with the checksum of what is being packed
+  ParamPtrs pp;
+  for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i) pp.p[i] = params[i];
+  if (int rc = launch_params_check(pp, precision, new_activation ? 1 : 0, packed, st)) return rc;
+  if (precision == SNB_PREC_FP32) return launch_pack_fp32(params, new_activation ? 1 : 0, packed, only_if_dirty, st);
+  return launch_pack_tc(params, precision, new_activation ? 1 : 0, packed, only_if_dirty, st);
+}
+
+int snb_pack_weights(const float* const* params, int precision, int new_activation, void* packed, void* stream) {
+  return pack_weights_impl("snb_pack_weights", params, precision, new_activation, packed, 0, stream);
+}
+
+int snb_refresh_weights(const float* const* params, int precision, int new_activation, void* packed, void* stream) {
+  return pack_weights_impl("snb_refresh_weights", params, precision, new_activation, packed, 1, stream);
 }
 
 int snb_sample_coarse(const float* rays, const float* z_steps, const float* perturb_u, float perturb, int use_disp,
@@ -158,7 +186,27 @@ int snb_composite_forward(const float* raw, int raw_channels, const float* z_val
   SNB_REQUIRE(raw_channels == 1 || aligned16(raw), "snb_composite_forward: raw must be 16-byte aligned");
   const float* nz = (noise_std != 0.f) ? noise : nullptr;
   return launch_composite(raw, raw_channels, z_vals, rays, nz, noise_std, white_back, n_rays, n_samples, rgb,
-                          depth, weights, reinterpret_cast<cudaStream_t>(stream));
+                          depth, weights, nullptr, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static int check_loss_spec(const char* who, const SnbLossSpec* loss) {
+  SNB_REQUIRE(loss != nullptr, "%s: null loss spec", who);
+  SNB_REQUIRE(loss->target_rgb != nullptr || loss->target_depth != nullptr, "%s: the loss spec has no target", who);
+  return SNB_OK;
+}
+
+int snb_composite_forward_loss(const float* raw, const float* z_vals, const float* rays, const float* noise,
+                               float noise_std, int white_back, int64_t n_rays, int n_samples,
+                               const SnbLossSpec* loss, float* rgb, float* depth, float* weights, float* loss_out,
+                               float* loss_ws, void* stream) {
+  SNB_REQUIRE(n_rays >= 0 && n_samples >= 1, "snb_composite_forward_loss: bad extents");
+  if (int rc = check_loss_spec("snb_composite_forward_loss", loss)) return rc;
+  SNB_REQUIRE(loss_out != nullptr && loss_ws != nullptr, "snb_composite_forward_loss: null loss output / workspace");
+  SNB_REQUIRE(n_rays == 0 || (raw && z_vals && rays && weights && rgb && depth), "snb_composite_forward_loss: null pointer");
+  SNB_REQUIRE(aligned16(raw), "snb_composite_forward_loss: raw must be 16-byte aligned");
+  const float* nz = (noise_std != 0.f) ? noise : nullptr;
+  return launch_composite(raw, 4, z_vals, rays, nz, noise_std, white_back, n_rays, n_samples, rgb, depth, weights,
+                          loss, loss_out, loss_ws, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int snb_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride, const float* u,
@@ -219,7 +267,26 @@ int snb_composite_backward(const float* raw, const float* z_vals, const float* r
   SNB_REQUIRE(aligned16(raw) && aligned16(g_raw), "snb_composite_backward: raw / g_raw must be 16-byte aligned");
   const float* nz = (noise_std != 0.f) ? noise : nullptr;
   return launch_composite_bwd(raw, z_vals, rays, nz, noise_std, white_back, g_rgb, g_depth, g_weights, n_rays,
-                              n_samples, g_raw, reinterpret_cast<cudaStream_t>(stream));
+                              n_samples, g_raw, nullptr, nullptr, nullptr, nullptr, nullptr,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int snb_composite_backward_loss(const float* raw, const float* z_vals, const float* rays, const float* noise,
+                                float noise_std, int white_back, const float* g_rgb, const float* g_depth,
+                                const float* g_weights, const SnbLossSpec* loss, const float* rgb, const float* depth,
+                                const float* g_loss, int64_t n_rays, int n_samples, float* g_raw, float* g_amax,
+                                void* stream) {
+  SNB_REQUIRE(n_rays >= 0 && n_samples >= 1, "snb_composite_backward_loss: bad extents");
+  SNB_REQUIRE(n_rays == 0 || (raw && z_vals && rays && g_raw), "snb_composite_backward_loss: null pointer");
+  SNB_REQUIRE(aligned16(raw) && aligned16(g_raw), "snb_composite_backward_loss: raw / g_raw must be 16-byte aligned");
+  if (loss != nullptr) {
+    if (int rc = check_loss_spec("snb_composite_backward_loss", loss)) return rc;
+    SNB_REQUIRE(n_rays == 0 || ((loss->target_rgb == nullptr || rgb) && (loss->target_depth == nullptr || depth)),
+                "snb_composite_backward_loss: the forward's rgb / depth outputs are required with a loss spec");
+  }
+  const float* nz = (noise_std != 0.f) ? noise : nullptr;
+  return launch_composite_bwd(raw, z_vals, rays, nz, noise_std, white_back, g_rgb, g_depth, g_weights, n_rays,
+                              n_samples, g_raw, loss, rgb, depth, g_loss, g_amax, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int snb_field_backward(const float* const* params, float* const* grads, int new_activation, const float* g_raw,
@@ -234,6 +301,22 @@ int snb_field_backward(const float* const* params, float* const* grads, int new_
               "snb_field_backward: null pointer");
   return field_backward_fp32(params, grads, new_activation, g_raw, raw, save_enc, save_dir, save_h, save_g,
                              n_points, ws_a, ws_b, ws_s, ws_w, ws_m, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int snb_adam_step(float* const* params, const float* const* grads, float* exp_avg, float* exp_avg_sq,
+                  const SnbAdamArgs* args, int precision, int new_activation, void* packed, void* stream) {
+  SNB_REQUIRE(params && grads && exp_avg && exp_avg_sq && args, "snb_adam_step: null pointer");
+  for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i) SNB_REQUIRE(params[i] != nullptr, "snb_adam_step: parameter tensor %d is null", i);
+  SNB_REQUIRE(args->step >= 1, "snb_adam_step: step counts from 1 (got %d)", args->step);
+  SNB_REQUIRE(args->lr >= 0. && args->eps >= 0. && args->beta1 >= 0. && args->beta1 < 1. && args->beta2 >= 0. &&
+                  args->beta2 < 1. && args->weight_decay >= 0.,
+              "snb_adam_step: invalid hyper-parameters");
+  SNB_REQUIRE(packed == nullptr || aligned16(packed), "snb_adam_step: packed image must be 16-byte aligned");
+  if (packed != nullptr)
+    if (int rc = check_precision(precision)) return rc;
+  static_assert(SNB_PARAM_FLOATS == 593408 + 2436, "parameter count");
+  return adam_step_pack(params, grads, exp_avg, exp_avg_sq, *args, precision, new_activation, packed,
+                        reinterpret_cast<cudaStream_t>(stream));
 }
 
 int snb_render_forward(const SnbRenderArgs* a, void* stream) {

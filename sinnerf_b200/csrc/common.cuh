@@ -15,6 +15,25 @@ void set_error(const std::string& msg);
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
 
+// ------------------------------------------------------------------ per-device launch state (host)
+// The library may be driven on several GPUs from one process (one device current per call): SM counts and
+// the opt-in dynamic-shared-memory attribute are per DEVICE, so both are cached per device ordinal.
+constexpr int kMaxDevices = 64;
+int current_device();   // ordinal of the current CUDA device
+int sm_count();         // its SM count (cached per ordinal)
+struct SmemOptIn {      // one zero-initialised static per kernel instantiation
+  int bytes[kMaxDevices];
+};
+template <class Kernel>
+inline int ensure_smem(Kernel kernel, SmemOptIn& st, int bytes, const char* what) {
+  const int dev = current_device() & (kMaxDevices - 1);
+  if (st.bytes[dev] >= bytes) return SNB_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e));
+  st.bytes[dev] = bytes;
+  return SNB_OK;
+}
+
 #define SNB_REQUIRE(cond, ...)                           \
   do {                                                   \
     if (!(cond)) return ::snb::fail(SNB_ERR_INVALID, __VA_ARGS__); \
@@ -49,10 +68,31 @@ struct PackedHeader {
   uint32_t magic;      // 'SNBW'
   int32_t precision;   // SNB_PREC_*
   int32_t new_activation;
-  int32_t reserved[61];
+  int32_t cta_group;
+  // snb_refresh_weights: a position-dependent 64-bit checksum of the 24 fp32 parameter tensors the image was
+  // packed from.  The check kernel recomputes it on the device and sets `dirty`; the pack kernels of a
+  // refresh return immediately when it is 0 -- no host round trip, and in-place updates that bypass
+  // autograd's version counter (`p.data.copy_`, reference utils/optimizers.py:98,180,268) are still seen.
+  int32_t dirty;
+  uint32_t blocks_done;          // scratch of the check kernel (self-resetting)
+  unsigned long long checksum;
+  unsigned long long partial;    // scratch of the check kernel (self-resetting)
+  int32_t reserved[54];
 };
 static_assert(sizeof(PackedHeader) == 256, "header is 256 B so payloads stay 256-B aligned");
 constexpr uint32_t kMagic = 0x57424e53u;
+
+// element counts of the 24 parameter tensors in state-dict order (weight, bias per layer)
+__host__ __device__ constexpr int param_numel(int i) {
+  // weights: l0 256x63, l1-3 256x256, l4 256x319, l5-7 256x256, final 256x256, dir 128x283, sigma 1x256, rgb 3x128
+  return (i & 1) ? (i < 18 ? 256 : (i == 19 ? 128 : (i == 21 ? 1 : 3)))
+                 : (i == 0 ? 256 * 63 : (i == 8 ? 256 * 319 : (i < 18 ? 256 * 256 : (i == 18 ? 128 * 283 : (i == 20 ? 256 : 384)))));
+}
+struct ParamPtrs {
+  const float* p[SNB_N_PARAM_TENSORS];
+};
+// enqueues the check kernel: header.dirty = (image was not packed from exactly these values / this mode)
+int launch_params_check(const ParamPtrs& pp, int precision, int new_activation, void* image, cudaStream_t st);
 
 // ------------------------------------------------------------------ fp32 (FFMA) image
 // floats after the header:

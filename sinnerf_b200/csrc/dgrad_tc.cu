@@ -259,16 +259,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
 
 template <int NRED>
 int launch_dgrad_tc(const DgradTcArgs& a, cudaStream_t st) {
-  static bool configured = false;
+  static SmemOptIn optin;
   const int smem = (int)sizeof(DgSmem<NRED>) + 1024;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dgrad_tc_kernel<NRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(dgrad_tc): %s", cudaGetErrorString(e));
-    configured = true;
-  }
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (int rc = ensure_smem(dgrad_tc_kernel<NRED>, optin, smem, "dgrad_tc")) return rc;
+  const int sms = sm_count();
   const long long ntiles = (a.P + kDgTile - 1) / kDgTile;
   long long pairs = (ntiles + 1) / 2;
   if (pairs > sms / 2) pairs = sms / 2;

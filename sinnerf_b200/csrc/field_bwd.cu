@@ -325,15 +325,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadArgs a) {
 // ------------------------------------------------------------------------------------------
 // host: the whole MLP backward of one render pass
 // ------------------------------------------------------------------------------------------
-static int dev_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sms;
-}
+static int dev_sms() { return sm_count(); }
 
 // wgrad_tc.cu: the same contraction on tensor cores (bf16 hi/lo split, fp32 accumulate in TMEM)
 int run_wgrad_tc(const float* dY, int N, const float* X, int ldx, int K, float* dW, int ldw, int col_off, float* db,
@@ -370,12 +362,8 @@ static int run_dgrad(const float* dY, int N, const float* W, int ldw, int col_of
                      const uint32_t* mask_bits, const float* extra, int extra_stride, const float* evec, float* dX,
                      long long P, cudaStream_t st) {
   if (!bwd_simt()) return run_dgrad_tc(dY, N, W, ldw, col_off, mask_bits, extra, extra_stride, evec, dX, P, st);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DgradSmem));
-    if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(dgrad): %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_smem(dgrad_kernel, optin, (int)sizeof(DgradSmem), "dgrad")) return rc;
   DgradArgs a{dY, N, W, ldw, col_off, mask, extra, extra_stride, evec, dX, P};
   const long long ntiles = (P + 127) / 128;
   const int grid = (int)(ntiles < dev_sms() ? ntiles : dev_sms());

@@ -306,26 +306,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_simt_kernel(FieldParams p) 
 }
 
 // ------------------------------------------------------------------ host launchers
-static int g_sm_count = 0;
-static int sm_count() {
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return g_sm_count;
-}
-
 template <bool kEmbedded>
 static int launch_field_simt(const FieldParams& p, cudaStream_t st) {
-  static bool configured = false;
+  static SmemOptIn optin;
   const size_t smem = sizeof(FieldSmem);
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(field_simt_kernel<kEmbedded>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(field_simt): %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  if (int rc = ensure_smem(field_simt_kernel<kEmbedded>, optin, (int)smem, "field_simt")) return rc;
   const long long ntiles = (p.n_points + TM - 1) / TM;
   if (ntiles == 0) return SNB_OK;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());

@@ -169,15 +169,15 @@ __host__ __device__ constexpr ChunkTable make_chunk_table() {
   t.steps_total = off;
   return t;
 }
-__constant__ ChunkTable c_chunks_cg1 = make_chunk_table<32>();
 __constant__ ChunkTable c_chunks_cg2 = make_chunk_table<128>();
-static constexpr ChunkTable h_chunks_cg1 = make_chunk_table<32>();
 static constexpr ChunkTable h_chunks_cg2 = make_chunk_table<128>();
-static_assert(h_chunks_cg1.n_total == 129 && h_chunks_cg1.n_sigma_only == 120, "chunk schedule (K32)");
 static_assert(h_chunks_cg2.n_total == 35 && h_chunks_cg2.n_sigma_only == 32, "chunk schedule (K128)");
-static_assert(h_chunks_cg1.steps_total == h_chunks_cg2.steps_total && h_chunks_cg1.steps_total == 258, "K16 steps per tile");
+static_assert(h_chunks_cg2.steps_total == 258, "K16 steps per tile");
 template <int kCg>
-__device__ __forceinline__ const ChunkTable& chunk_table() { return kCg == 2 ? c_chunks_cg2 : c_chunks_cg1; }
+__device__ __forceinline__ const ChunkTable& chunk_table() {
+  static_assert(kCg == 2, "only CTA pairs are built");
+  return c_chunks_cg2;
+}
 
 // number of waits on barrier code `code` (WAIT_*) in chunks [0, ci) -- plus chunk ci's own `wait` when
 // the question is about its mid-chunk wait.  a_ready[q] completes once per layer epilogue, 8 per
@@ -205,10 +205,6 @@ __device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int
 }
 template <int N, class F>
 __device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
-
-// cta_group used by the tensor-core path.  The kernels stay templated on it (Geo<1> is the
-// single-CTA geometry the CTA-pair design was derived from) but only pairs are instantiated.
-static int tc_cta_group() { return 2; }
 
 // ------------------------------------------------------------------ packed image
 // [PackedHeader 256 B][consts: biases + head weights, fp32][chunk 0][chunk 1]...
@@ -331,12 +327,11 @@ __device__ __forceinline__ float softplus_fast(float s) {
 }
 
 // ------------------------------------------------------------------ pack kernel
-struct ParamPtrsTc {
-  const float* p[SNB_N_PARAM_TENSORS];
-};
+using ParamPtrsTc = ParamPtrs;
 
 // W'[n][k] = sum_j Wd[n][j] Wf[j][k],  b'[n] = bd[n] + sum_j Wd[n][j] bf[j]   (double accumulation)
-__global__ void fuse_bottleneck_kernel(ParamPtrsTc pp, float* fused) {
+__global__ void fuse_bottleneck_kernel(ParamPtrsTc pp, float* fused, const PackedHeader* hdr, int only_if_dirty) {
+  if (only_if_dirty && !hdr->dirty) return;
   const float* Wd = pp.p[18];   // (128, 283)
   const float* Wf = pp.p[16];   // (256, 256)
   const float* bf = pp.p[17];
@@ -351,11 +346,12 @@ __global__ void fuse_bottleneck_kernel(ParamPtrsTc pp, float* fused) {
 }
 
 template <bool kBf16, bool kSplit, int kCg>
-__global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation, unsigned char* image) {
+__global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation, unsigned char* image, int only_if_dirty) {
   using G = Geo<kCg>;
   constexpr ConstLayout CL = make_const_layout();
   const ChunkTable& tab = chunk_table<kCg>();
   PackedHeader* hdr = reinterpret_cast<PackedHeader*>(image);
+  if (only_if_dirty && !hdr->dirty) return;
   float* cst = reinterpret_cast<float*>(image + sizeof(PackedHeader));
   unsigned char* chunks = image + sizeof(PackedHeader) + kConstBytes;
   const float* fused = reinterpret_cast<const float*>(chunks + chunks_bytes(precision));   // fuse_bottleneck_kernel
@@ -364,7 +360,7 @@ __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation
     hdr->magic = kMagic;
     hdr->precision = precision;
     hdr->new_activation = new_activation;
-    hdr->reserved[0] = kCg;
+    hdr->cta_group = kCg;
   }
   for (int e = gtid; e < kConstFloats; e += gsz) {
     float v = 0.f;
@@ -413,24 +409,25 @@ __global__ void pack_tc_kernel(ParamPtrsTc pp, int precision, int new_activation
 
 template <int kCg>
 static int launch_pack_tc_cg(const ParamPtrsTc& pp, int precision, int new_activation, unsigned char* img,
-                             cudaStream_t st) {
+                             int only_if_dirty, cudaStream_t st) {
   if (precision < SNB_PREC_F16X3 || precision > SNB_PREC_BF16)
     return fail(SNB_ERR_INVALID, "launch_pack_tc: precision %d is not a tensor-core mode", precision);
   float* fused = reinterpret_cast<float*>(img + sizeof(PackedHeader) + kConstBytes + chunks_bytes(precision));
-  fuse_bottleneck_kernel<<<148, 256, 0, st>>>(pp, fused);
+  fuse_bottleneck_kernel<<<148, 256, 0, st>>>(pp, fused, reinterpret_cast<const PackedHeader*>(img), only_if_dirty);
   if (int rc = check_launch("fuse_bottleneck_kernel")) return rc;
-  if (precision == SNB_PREC_F16X3) pack_tc_kernel<false, true, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
-  else if (precision == SNB_PREC_BF16X3) pack_tc_kernel<true, true, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
-  else if (precision == SNB_PREC_BF16) pack_tc_kernel<true, false, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img);
+  if (precision == SNB_PREC_F16X3) pack_tc_kernel<false, true, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img, only_if_dirty);
+  else if (precision == SNB_PREC_BF16X3) pack_tc_kernel<true, true, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img, only_if_dirty);
+  else if (precision == SNB_PREC_BF16) pack_tc_kernel<true, false, kCg><<<296, 256, 0, st>>>(pp, precision, new_activation, img, only_if_dirty);
   else return fail(SNB_ERR_INVALID, "launch_pack_tc: precision %d is not a tensor-core mode", precision);
   return check_launch("pack_tc_kernel");
 }
 
-int launch_pack_tc(const float* const* params, int precision, int new_activation, void* image, cudaStream_t st) {
+int launch_pack_tc(const float* const* params, int precision, int new_activation, void* image, int only_if_dirty,
+                   cudaStream_t st) {
   ParamPtrsTc pp;
   for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i) pp.p[i] = params[i];
   unsigned char* img = reinterpret_cast<unsigned char*>(image);
-  return launch_pack_tc_cg<2>(pp, precision, new_activation, img, st);
+  return launch_pack_tc_cg<2>(pp, precision, new_activation, img, only_if_dirty, st);
 }
 
 // ------------------------------------------------------------------ shared memory
@@ -986,19 +983,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 // ------------------------------------------------------------------ host
 template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, bool kTrain = false>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
-  static bool configured = false;
+  static SmemOptIn optin;
   const long long ntiles = (p.n_points + kTile - 1) / kTile;
   if (ntiles == 0) return SNB_OK;       // an empty pass is a no-op: no CUDA call at all
   const size_t smem = sizeof(TcSmem<kSplit, kCg, kTrain>) + 1024;
   auto kern = field_tc_kernel<kBf16, kSplit, kEmbedded, kCg, kTrain>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(field_tc): %s", cudaGetErrorString(e));
-    configured = true;
-  }
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (int rc = ensure_smem(kern, optin, (int)smem, "field_tc")) return rc;
+  const int sms = sm_count();
   long long groups = (ntiles + kCg - 1) / kCg;
   if (groups > sms / kCg) groups = sms / kCg;
   static const int debug = getenv("SNB_TC_DEBUG") ? atoi(getenv("SNB_TC_DEBUG")) : 0;

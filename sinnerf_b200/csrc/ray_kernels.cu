@@ -171,14 +171,31 @@ __global__ void __launch_bounds__(256) embed3_kernel(const float* __restrict__ x
 // One warp per ray; 32 samples per step; inclusive product scan by shuffles, carried across
 // steps; the exclusive product is the scan shifted by one lane.
 // ---------------------------------------------------------------------------------------
+// Per-ray training losses folded into the compositing (reference losses.py:12-22 MSELoss,
+// models/sinnerf.py:32-42 SL1Loss, consumed at models/sinnerf.py:310-319):
+//   loss[0] = sum_ray wr[ray] * sum_c (rgb_c - target_rgb_c)^2      (wr = 1 / (3 N) gives nn.MSELoss 'mean')
+//   loss[1] = sum_ray wd[ray] * smooth_l1(depth - target_depth)     (wd = 1 / N gives nn.SmoothL1Loss 'mean', beta 1)
+// Reduction: warp partials -> block partial (fixed order) -> ws; the last block to finish adds the block
+// partials in index order, so the value is deterministic for a given grid.
+struct LossSpec {
+  const float* trgb;     // (N,3) nullable
+  const float* tdepth;   // (N,)  nullable
+  const float* wr;       // (N,) nullable -> wr0
+  const float* wd;       // (N,) nullable -> wd0
+  float wr0, wd0;
+};
+__device__ __forceinline__ float smooth_l1(float x) { const float a = fabsf(x); return a < 1.0f ? 0.5f * x * x : a - 0.5f; }
+__device__ __forceinline__ float smooth_l1_grad(float x) { return fabsf(x) < 1.0f ? x : (x > 0.f ? 1.0f : -1.0f); }
+
 __global__ void __launch_bounds__(256) composite_fwd_kernel(
     const float* __restrict__ raw, int raw_channels, const float* __restrict__ z_vals,
     const float* __restrict__ rays, const float* __restrict__ noise, float noise_std, int white_back,
     long long n_rays, int S, float* __restrict__ rgb_out, float* __restrict__ depth_out,
-    float* __restrict__ w_out) {
+    float* __restrict__ w_out, LossSpec ls, float* __restrict__ loss_out, float* __restrict__ loss_ws) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float loss_rgb = 0.f, loss_depth = 0.f;      // lane 0: this warp's share of the two loss sums
   for (long long ray = warp; ray < n_rays; ray += nwarps) {
     const float dx = rays[ray * 8 + 3], dy = rays[ray * 8 + 4], dz = rays[ray * 8 + 5];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.norm(dir_, dim=-1)
@@ -239,9 +256,44 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(
             ab = __fsub_rn(__fadd_rn(ab, 1.0f), aw);
           }
           rgb_out[ray * 3 + 0] = ar; rgb_out[ray * 3 + 1] = ag; rgb_out[ray * 3 + 2] = ab;
+          if (ls.trgb != nullptr) {
+            const float e0 = ar - ls.trgb[ray * 3], e1 = ag - ls.trgb[ray * 3 + 1], e2 = ab - ls.trgb[ray * 3 + 2];
+            loss_rgb = fmaf(ls.wr != nullptr ? ls.wr[ray] : ls.wr0, e0 * e0 + e1 * e1 + e2 * e2, loss_rgb);
+          }
         }
-        if (depth_out != nullptr) depth_out[ray] = ad;
+        if (depth_out != nullptr) {
+          depth_out[ray] = ad;
+          if (ls.tdepth != nullptr)
+            loss_depth = fmaf(ls.wd != nullptr ? ls.wd[ray] : ls.wd0, smooth_l1(ad - ls.tdepth[ray]), loss_depth);
+        }
       }
+    }
+  }
+  if (loss_out != nullptr) {
+    __shared__ float part[8][2];
+    __shared__ bool last;
+    if (lane == 0) { part[threadIdx.x >> 5][0] = loss_rgb; part[threadIdx.x >> 5][1] = loss_depth; }
+    __syncthreads();
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(loss_ws);
+    float* partials = loss_ws + 4;
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int i = 0; i < 8; ++i) { a += part[i][0]; b += part[i][1]; }
+      partials[2 * blockIdx.x] = a; partials[2 * blockIdx.x + 1] = b;
+      __threadfence();
+      last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 32) {
+      __threadfence();
+      // fixed-order sum: lane l adds blocks l, l+32, ...; then a fixed shuffle tree
+      float a = 0.f, b = 0.f;
+      for (unsigned int i = lane; i < gridDim.x; i += 32) {
+        a += __ldcg(partials + 2 * i); b += __ldcg(partials + 2 * i + 1);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(kFull, a, off); b += __shfl_xor_sync(kFull, b, off); }
+      if (lane == 0) { loss_out[0] = a; loss_out[1] = b; *ticket = 0u; }
     }
   }
 }
@@ -261,8 +313,10 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
     const float* __restrict__ raw, const float* __restrict__ z_vals, const float* __restrict__ rays,
     const float* __restrict__ noise, float noise_std, int white_back, const float* __restrict__ g_rgb,
     const float* __restrict__ g_depth, const float* __restrict__ g_w, long long n_rays, int S,
-    float* __restrict__ g_raw) {
+    float* __restrict__ g_raw, LossSpec ls, const float* __restrict__ out_rgb, const float* __restrict__ out_depth,
+    const float* __restrict__ g_loss, unsigned int* __restrict__ g_amax) {
   extern __shared__ float sm[];   // per warp: alpha[S], T[S], gwv[S] (= gw_i * w_i, then its suffix sums)
+  float amax = 0.f;               // max |g_raw| written by this thread (for the 16-bit backward's scaling)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float* sa = sm + (size_t)wib * 3 * S;
   float* sT = sa + S;
@@ -276,6 +330,17 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
     float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f;
     if (g_rgb != nullptr) { gr = g_rgb[ray * 3]; gg = g_rgb[ray * 3 + 1]; gb = g_rgb[ray * 3 + 2]; }
     if (g_depth != nullptr) gd = g_depth[ray];
+    // fused losses: d loss[0] / d rgb_c = 2 wr (rgb_c - t_c), d loss[1] / d depth = wd smooth_l1'(depth - t)
+    if (ls.trgb != nullptr) {
+      const float k = 2.0f * (ls.wr != nullptr ? ls.wr[ray] : ls.wr0) * (g_loss != nullptr ? g_loss[0] : 1.0f);
+      gr = fmaf(k, out_rgb[ray * 3] - ls.trgb[ray * 3], gr);
+      gg = fmaf(k, out_rgb[ray * 3 + 1] - ls.trgb[ray * 3 + 1], gg);
+      gb = fmaf(k, out_rgb[ray * 3 + 2] - ls.trgb[ray * 3 + 2], gb);
+    }
+    if (ls.tdepth != nullptr) {
+      const float k = (ls.wd != nullptr ? ls.wd[ray] : ls.wd0) * (g_loss != nullptr ? g_loss[1] : 1.0f);
+      gd = fmaf(k, smooth_l1_grad(out_depth[ray] - ls.tdepth[ray]), gd);
+    }
     const float gwb = white_back ? (gr + gg + gb) : 0.f;
     // forward recompute + gw_i w_i
     float carry = 1.0f;
@@ -339,8 +404,15 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
       const float e = expf(-__fmul_rn(delta, fmaxf(sgm, 0.f)));
       const float gsig = sgm > 0.f ? galpha * delta * e : 0.f;
       reinterpret_cast<float4*>(g_raw)[ray * S + i] = make_float4(gr * w, gg * w, gb * w, gsig);
+      amax = fmaxf(fmaxf(amax, fabsf(gsig)), fmaxf(fmaxf(fabsf(gr * w), fabsf(gg * w)), fabsf(gb * w)));
     }
     __syncwarp();
+  }
+  if (g_amax != nullptr) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(kFull, amax, off));
+    // non-negative floats order like their bit patterns; NaN / inf gradients saturate the statistic
+    if (lane == 0 && amax > 0.f) atomicMax(g_amax, __float_as_uint(amax == amax ? fminf(amax, 3.0e38f) : 3.0e38f));
   }
 }
 
@@ -437,11 +509,39 @@ __global__ void __launch_bounds__(128) importance_merge_kernel(
       if (z_new_out != nullptr) z_new_out[ray * Ni + j] = zn;
     }
     __syncwarp();
-    // sorted union (torch.sort(cat([z, z_new]))).  The coarse depths are sorted; the new ones are
-    // rank-sorted first (random u: any order; det u: already monotone up to an ulp at bin edges).
-    // Then every element's position is its own index plus a binary-search count in the other list
-    // (ties: coarse first).  O(Ni^2 + F log F) instead of the O(F^2) all-pairs rank.
+    // sorted union (torch.sort(cat([z, z_new]))).  The coarse depths are sorted whenever near <= far and
+    // everything is finite; the new ones are rank-sorted first (random u: any order; det u: already monotone
+    // up to an ulp at bin edges).  Then every element's position is its own index plus a binary-search count
+    // in the other list (ties: coarse first).  O(Ni^2 + F log F) instead of the O(F^2) all-pairs rank.
     float* zn = zs + S;
+    {
+      // precondition of the merge: coarse row ascending, no NaN anywhere.  Rays with near > far, or NaN / inf
+      // depths (near = 0 with use_disp), take the general path: an all-pairs rank sort of the S + Ni values
+      // with torch.sort's order (ascending, NaN last) -- every slot of z_fine is written in either case.
+      bool ok = true;
+      for (int i = lane; i < F; i += 32) {
+        const float v = zs[i];
+        if (v != v) ok = false;
+        if (i + 1 < S && !(v <= zs[i + 1])) ok = false;
+      }
+      if (!__all_sync(kFull, ok)) {
+        for (int e = lane; e < F; e += 32) {
+          const float v = zs[e];
+          const bool vn = v != v;
+          int r = 0;
+          for (int k = 0; k < F; ++k) {
+            const float o = zs[k];
+            const bool on = o != o;
+            const bool less = vn ? !on : (o < v);
+            const bool same = vn ? on : (o == v);
+            r += less || (same && k < e);
+          }
+          z_fine[ray * F + r] = v;
+        }
+        __syncwarp();
+        continue;
+      }
+    }
     {
       float mine[8];                       // Ni <= 256
       int rk[8];
@@ -475,13 +575,62 @@ __global__ void __launch_bounds__(128) importance_merge_kernel(
 // ---------------------------------------------------------------------------------------
 // weight packing (fp32 image)
 // ---------------------------------------------------------------------------------------
-struct ParamPtrs {
-  const float* p[SNB_N_PARAM_TENSORS];
-};
+// ---------------------------------------------------------------------------------------
+// params_check: 64-bit position-dependent checksum of the 24 parameter tensors vs the one stored in the
+// image header (snb_refresh_weights).  2.4 MB of L2/HBM reads, one launch; the last block to finish
+// compares, sets header.dirty and resets the scratch fields.
+// ---------------------------------------------------------------------------------------
+constexpr int kCheckBlocks = 64;
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) params_check_kernel(ParamPtrs pp, int precision, int new_activation,
+                                                           PackedHeader* hdr) {
+  unsigned long long h = 0;
+  unsigned long long base = 0;
+  for (int t = 0; t < SNB_N_PARAM_TENSORS; ++t) {
+    const int n = param_numel(t);
+    const unsigned int* w = reinterpret_cast<const unsigned int*>(pp.p[t]);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+      h += mix64(((base + e) << 32) ^ (unsigned long long)w[e] ^ 0x9e3779b97f4a7c15ull);
+    base += n;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(kFull, h, off);
+  __shared__ unsigned long long part[8];
+  __shared__ bool last;
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long b = 0;
+    for (int i = 0; i < 8; ++i) b += part[i];
+    atomicAdd(&hdr->partial, b);
+    __threadfence();
+    last = atomicAdd(&hdr->blocks_done, 1u) == gridDim.x - 1;
+    if (last) {
+      __threadfence();
+      const unsigned long long total = atomicAdd(&hdr->partial, 0ull);
+      hdr->dirty = (hdr->magic != kMagic || hdr->precision != precision || hdr->new_activation != new_activation ||
+                    hdr->checksum != total) ? 1 : 0;
+      hdr->checksum = total;
+      hdr->partial = 0ull;
+      hdr->blocks_done = 0u;
+    }
+  }
+}
 
-__global__ void pack_fp32_kernel(ParamPtrs pp, int new_activation, unsigned char* image) {
+int launch_params_check(const ParamPtrs& pp, int precision, int new_activation, void* image, cudaStream_t st) {
+  params_check_kernel<<<kCheckBlocks, 256, 0, st>>>(pp, precision, new_activation, reinterpret_cast<PackedHeader*>(image));
+  return check_launch("params_check_kernel");
+}
+
+// only_if_dirty: part of a refresh -- return at once unless the check kernel flagged the image stale
+__global__ void pack_fp32_kernel(ParamPtrs pp, int new_activation, unsigned char* image, int only_if_dirty) {
   constexpr Fp32Layout L = make_fp32_layout();
   PackedHeader* hdr = reinterpret_cast<PackedHeader*>(image);
+  if (only_if_dirty && !hdr->dirty) return;
   float* W = reinterpret_cast<float*>(image + sizeof(PackedHeader));
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     hdr->magic = kMagic;
@@ -524,15 +673,7 @@ static int grid_for(long long work_items, int per_block, int cap_blocks) {
   if (b < 1) b = 1;
   return (int)(b < cap_blocks ? b : cap_blocks);
 }
-static int device_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sms;
-}
+static int device_sms() { return sm_count(); }
 
 int launch_sample_coarse(const float* rays, const float* z_steps, const float* perturb_u, float perturb,
                          int use_disp, int64_t n_rays, int S, float* z, cudaStream_t st) {
@@ -565,42 +706,52 @@ int launch_embed(const float* x, int64_t n, int C, int L, float* out, cudaStream
   }
   const size_t smem = (size_t)kEmbedRows * C * (2 * L + 1) * sizeof(float);
   if (smem > 200 * 1024) return fail(SNB_ERR_UNSUPPORTED, "snb_embed: C*(2L+1) too large for the smem tile");
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(embed): %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  if (smem > 48 * 1024)
+    if (int rc = ensure_smem(embed_kernel, optin, (int)smem, "embed")) return rc;
   const int grid = grid_for(n, kEmbedRows, device_sms() * 4);
   embed_kernel<<<grid, 256, smem, st>>>(x, n, C, L, out);
   return check_launch("embed_kernel");
 }
 
+static LossSpec make_loss_spec(const SnbLossSpec* l) {
+  LossSpec ls{};
+  if (l != nullptr) {
+    ls.trgb = l->target_rgb; ls.tdepth = l->target_depth; ls.wr = l->rgb_weight; ls.wd = l->depth_weight;
+    ls.wr0 = l->rgb_weight0; ls.wd0 = l->depth_weight0;
+  }
+  return ls;
+}
+
 int launch_composite(const float* raw, int raw_channels, const float* z, const float* rays, const float* noise,
                      float noise_std, int white_back, int64_t n_rays, int S, float* rgb, float* depth,
-                     float* w, cudaStream_t st) {
-  if (n_rays == 0) return SNB_OK;
-  const int grid = grid_for(n_rays, 8, device_sms() * 8);
+                     float* w, const SnbLossSpec* loss, float* loss_out, float* loss_ws, cudaStream_t st) {
+  if (n_rays == 0) {
+    if (loss_out != nullptr) return cudaMemsetAsync(loss_out, 0, 2 * sizeof(float), st) == cudaSuccess
+                                        ? SNB_OK : fail(SNB_ERR_CUDA, "cudaMemsetAsync(loss)");
+    return SNB_OK;
+  }
+  int grid = grid_for(n_rays, 8, device_sms() * 8);
+  if (loss_out != nullptr && grid > (SNB_LOSS_WS_FLOATS - 4) / 2) grid = (SNB_LOSS_WS_FLOATS - 4) / 2;
   composite_fwd_kernel<<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays,
-                                             S, rgb, depth, w);
+                                             S, rgb, depth, w, make_loss_spec(loss), loss_out, loss_ws);
   return check_launch("composite_fwd_kernel");
 }
 
 int launch_composite_bwd(const float* raw, const float* z, const float* rays, const float* noise, float noise_std,
                           int white_back, const float* g_rgb, const float* g_depth, const float* g_w, int64_t n_rays,
-                          int S, float* g_raw, cudaStream_t st) {
+                          int S, float* g_raw, const SnbLossSpec* loss, const float* out_rgb, const float* out_depth,
+                          const float* g_loss, float* g_amax, cudaStream_t st) {
   if (n_rays == 0) return SNB_OK;
   const size_t smem = (size_t)8 * 3 * S * sizeof(float);
   if (smem > 96 * 1024) return fail(SNB_ERR_UNSUPPORTED, "snb_composite_backward: too many samples per ray (%d)", S);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(composite_bwd): %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  if (smem > 48 * 1024)
+    if (int rc = ensure_smem(composite_bwd_kernel, optin, (int)smem, "composite_bwd")) return rc;
   const int grid = grid_for(n_rays, 8, device_sms() * 8);
   composite_bwd_kernel<<<grid, 256, smem, st>>>(raw, z, rays, noise, noise_std, white_back, g_rgb, g_depth, g_w,
-                                                n_rays, S, g_raw);
+                                                n_rays, S, g_raw, make_loss_spec(loss), out_rgb, out_depth, g_loss,
+                                                reinterpret_cast<unsigned int*>(g_amax));
   return check_launch("composite_bwd_kernel");
 }
 
@@ -629,10 +780,10 @@ int launch_importance_merge(const float* z_coarse, const float* w_coarse, const 
   return check_launch("importance_merge_kernel");
 }
 
-int launch_pack_fp32(const float* const* params, int new_activation, void* image, cudaStream_t st) {
+int launch_pack_fp32(const float* const* params, int new_activation, void* image, int only_if_dirty, cudaStream_t st) {
   ParamPtrs pp;
   for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i) pp.p[i] = params[i];
-  pack_fp32_kernel<<<device_sms() * 2, 256, 0, st>>>(pp, new_activation, reinterpret_cast<unsigned char*>(image));
+  pack_fp32_kernel<<<device_sms() * 2, 256, 0, st>>>(pp, new_activation, reinterpret_cast<unsigned char*>(image), only_if_dirty);
   return check_launch("pack_fp32_kernel");
 }
 

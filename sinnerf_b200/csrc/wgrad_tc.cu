@@ -268,25 +268,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(WgradTcArgs a) 
   if (warp == kWgMmaWarp) tmem_dealloc<G::kTmemCols>(tbase);
 }
 
-int wg_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sms;
-}
+int wg_sms() { return sm_count(); }
 
 template <int KP, int NM, int LDX>
 int launch_wgrad_tc(WgradTcArgs a, cudaStream_t st) {
   using G = WgGeo<KP, NM, LDX>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<KP, NM, LDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
-    if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "cudaFuncSetAttribute(wgrad_tc): %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_smem(wgrad_tc_kernel<KP, NM, LDX>, optin, G::kSmemBytes, "wgrad_tc")) return rc;
   int splits = wg_sms();
   long long rows = (a.P + splits - 1) / splits;
   rows = (rows + kWgBatch - 1) / kWgBatch * kWgBatch;

@@ -45,3 +45,40 @@ def render_rays_sharded(render_fn: Callable[[torch.Tensor], Dict[str, torch.Tens
     out = local.new_empty((per * world, 4))
     dist.all_gather_into_tensor(out, local, group=group)
     return out[:n]
+
+
+class PixelGather:
+    """Double-buffered, asynchronous all-gather of rendered pixel slabs for back-to-back frames.
+
+    A blocking `all_gather_into_tensor` after every frame makes the collective a per-step barrier: every rank
+    waits for the slowest one each step (measured in round 1 on 8 power-capped B200s: 61.9 -> 64.4 ms per step
+    while the render kernel itself moved 41.3 -> 41.7 ms).  Here gather k runs on NCCL's own stream while the
+    ranks already render frame k + 1; a rank only waits when it is TWO frames ahead (its buffer k - 2 is still
+    in flight).  `wait_all()` before reading the last results / stopping a clock."""
+
+    def __init__(self, rows_per_rank: int, device, group: Optional[dist.ProcessGroup] = None, depth: int = 2):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bufs = [torch.empty(rows_per_rank * self.world, 4, device=device) for _ in range(depth)]
+        self.works = [None] * depth
+        self.k = 0
+
+    def submit(self, local: torch.Tensor) -> torch.Tensor:
+        """Start gathering `local` ((rows_per_rank, 4), contiguous); returns the output buffer, valid after
+        the matching work completes (`wait_all()` or the submit that reuses this slot)."""
+        i = self.k % len(self.bufs)
+        self.k += 1
+        if self.works[i] is not None:
+            self.works[i].wait()          # stream-level wait: the current stream will not overwrite a gather in flight
+            self.works[i] = None
+        if self.world == 1:
+            self.bufs[i].copy_(local)
+            return self.bufs[i]
+        self.works[i] = dist.all_gather_into_tensor(self.bufs[i], local, group=self.group, async_op=True)
+        return self.bufs[i]
+
+    def wait_all(self) -> None:
+        for i, w in enumerate(self.works):
+            if w is not None:
+                w.wait()
+                self.works[i] = None

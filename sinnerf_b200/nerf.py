@@ -49,6 +49,10 @@ class Embedding(nn.Module):
             raise NotImplementedError("sinnerf_b200.Embedding: only logscale=True bands (the ones SinNeRF "
                                       "uses, models/sinnerf.py:131-132) have a kernel")
         _lib.require_device(x, "Embedding.forward")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("sinnerf_b200.Embedding.forward is not differentiable in its input (the reference "
+                                      "never differentiates it either: rays carry no grad, models/sinnerf.py:171-193); "
+                                      "call it under torch.no_grad() or detach the input")
         if x.dim() != 2 or x.shape[1] != self.in_channels:
             raise ValueError(f"Embedding.forward: expected (B, {self.in_channels}), got {tuple(x.shape)}")
         xc = x.detach().to(torch.float32).contiguous()
@@ -84,7 +88,7 @@ class NeRF(nn.Module):
             self.dir_encoding = nn.Sequential(nn.Linear(W + in_channels_dir, W // 2), nn.ReLU(True))
             self.sigma = nn.Linear(W, 1)
             self.rgb = nn.Sequential(nn.Linear(W // 2, 3), nn.Sigmoid())
-        self._packed = {}  # precision id -> (key, uint8 device tensor)
+        self._packed = {}  # (precision id, device) -> uint8 device tensor
 
     # ------------------------------------------------------------------ kernels' weight image
     def _check_shape(self):
@@ -104,23 +108,17 @@ class NeRF(nn.Module):
         return ps
 
     def packed_weights(self, precision=None) -> torch.Tensor:
-        """Device image of the weights in the layout the kernels stream (C ABI snb_pack_weights).
-        Cached; rebuilt when any parameter was modified in place (optimizer step, load_state_dict)
-        or moved."""
-        self._check_shape()
+        """Device image of the weights in the layout the kernels stream, brought up to date on the current
+        stream (C ABI snb_refresh_weights).  The image buffer is allocated once per (precision, device);
+        every call enqueues a check kernel that compares a checksum of the parameter VALUES with the one the
+        image was packed from and re-packs on the device only when they differ -- so optimizer steps,
+        `load_state_dict` and in-place updates through `p.data` (which do not bump `_version`; reference
+        utils/optimizers.py:98,180,268) are all seen, with no host synchronisation."""
         prec = _lib.precision_id(config.get_precision() if precision is None else precision)
+        image = self.packed_image_buffer(prec)
         ps = self._param_list()
         dev = ps[0].device
-        _lib.require_device(ps[0], "NeRF")
-        key = (str(dev),) + tuple((p.data_ptr(), p._version) for p in ps)
-        hit = self._packed.get(prec)
-        if hit is not None and hit[0] == key:
-            return hit[1]
         lib = _lib.load()
-        nbytes = lib.snb_packed_weights_bytes(prec)
-        if nbytes == 0:
-            raise NotImplementedError(f"precision mode {prec} is not available in this build")
-        image = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         srcs = []
         for p in ps:
             if p.dtype != torch.float32 or p.device != dev:
@@ -128,16 +126,43 @@ class NeRF(nn.Module):
             srcs.append(p.detach().contiguous())
         arr = (C.c_void_p * len(srcs))(*[s.data_ptr() for s in srcs])
         with torch.cuda.device(dev):
-            _lib.check(lib.snb_pack_weights(arr, prec, int(self.use_new_activation), _lib.ptr(image),
-                                            _lib.stream_ptr(dev)), "snb_pack_weights")
-        self._packed[prec] = (key, image)
+            _lib.check(lib.snb_refresh_weights(arr, prec, int(self.use_new_activation), _lib.ptr(image),
+                                               _lib.stream_ptr(dev)), "snb_refresh_weights")
         return image
+
+    def packed_image_buffer(self, prec: int) -> torch.Tensor:
+        """The (precision, device) image buffer, allocated zero-filled on first use; its CONTENT is brought up
+        to date by packed_weights() / FusedAdam.step()."""
+        self._check_shape()
+        ps = self._param_list()
+        dev = ps[0].device
+        _lib.require_device(ps[0], "NeRF")
+        key = (prec, str(dev))
+        image = self._packed.get(key)
+        if image is None:
+            nbytes = _lib.load().snb_packed_weights_bytes(prec)
+            if nbytes == 0:
+                raise NotImplementedError(f"precision mode {prec} is not available in this build")
+            image = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            self._packed = {k: v for k, v in self._packed.items() if k[1] == str(dev)}   # drop images of old devices
+            self._packed[key] = image
+        return image
+
+    def invalidate_packed(self) -> None:
+        """Forget every packed image (they are rebuilt on the next pass).  Never needed for correctness --
+        packed_weights() checks the parameter values itself -- only to release the buffers."""
+        self._packed = {}
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, sigma_only=False):
         """x (B, 63(+27)) embedded position (and direction) -> (B,4) [rgb, sigma], or (B,1) sigma
         -- reference models/nerf.py:105-148."""
         _lib.require_device(x, "NeRF.forward")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(
+                "sinnerf_b200.NeRF.forward runs the inference kernels and builds no autograd graph; gradients are "
+                "wired through render_rays (the only differentiated caller in the reference, models/sinnerf.py:171-193). "
+                "Call model(x) under torch.no_grad(), or train through render_rays.")
         need = self.in_channels_xyz if sigma_only else self.in_channels_xyz + self.in_channels_dir
         if x.dim() != 2 or x.shape[1] != need:
             raise ValueError(f"NeRF.forward: expected (B, {need}), got {tuple(x.shape)}")

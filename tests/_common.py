@@ -7,7 +7,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
 
-RENDER_CASES = ["c1_seed0_64p0", "lego_seed0_64p64_wb", "llff_room_64p64", "llff_room_64p64_train",
+RENDER_CASES = ["c1_seed0_64p0", "c1_full_seed0_64p0", "lego_seed0_64p64_wb", "llff_room_64p64", "llff_room_64p64_train",
                 "dtu_seed0_64p64_disp", "lego_room_testtime", "lego_seed0_32p16_odd"]
 
 

@@ -174,7 +174,17 @@ def rays_golden():
     print("wrote", path)
 
 
+def c1_full():
+    """BASELINE configs[0] in full: all 1 024 rays of the C1 case (the 128-ray prefix is render_c1_seed0_64p0)."""
+    seed_models = list(seeded_models(0))
+    render_case("c1_full_seed0_64p0", seed_models[:1], synthetic.random_rays("lego", 1024, seed=0),
+                n_importance=0, white_back=False)
+
+
 def main():
+    if "--only-c1-full" in sys.argv:
+        c1_full()
+        return
     room = load_room()
     if "--rays-only" in sys.argv:
         rays_golden()
@@ -255,6 +265,7 @@ def main():
                 perturb=0.5, noise_std=0.3, white_back=True)
     grad_golden(room)
     rays_golden()
+    c1_full()
 
 
 if __name__ == "__main__":

@@ -63,3 +63,36 @@ def test_sharded_render_equals_single_process(tmp_path, n_rays):
     assert outs[0].shape == (n_rays, 4)
     # slabs are rendered independently; per-ray results do not depend on the batch they ride in
     assert torch.allclose(outs[0], ref, rtol=0, atol=1e-6)
+
+
+def _gather_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sinnerf_b200.distributed import PixelGather
+    pg = PixelGather(5, torch.device("cpu"))
+    seen = []
+    outs = []
+    for frame in range(5):          # more frames than buffers: slots are reused only after their gather finished
+        local = torch.full((5, 4), float(10 * frame + rank))
+        outs.append((frame, pg.submit(local)))
+        if len(outs) == 2:           # consume the older result before its slot comes up again
+            f, buf = outs.pop(0)
+            pg.wait_all()
+            seen.append((f, buf.clone()))
+    pg.wait_all()
+    seen += [(f, b.clone()) for f, b in outs]
+    torch.save(seen, os.path.join(tmp, f"g{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_pixel_gather_double_buffering(tmp_path):
+    """PixelGather (the asynchronous, double-buffered all-gather behind the weak-scaling bench): every frame's
+    gathered buffer holds all ranks' slabs of THAT frame, in rank order, on every rank."""
+    world = 2
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        seen = torch.load(os.path.join(tmp_path, f"g{r}.pt"))
+        assert [f for f, _ in seen] == list(range(5))
+        for f, buf in seen:
+            assert buf.shape == (10, 4)
+            assert torch.equal(buf[:5], torch.full((5, 4), float(10 * f))) and torch.equal(buf[5:], torch.full((5, 4), float(10 * f + 1)))
