@@ -157,6 +157,26 @@ int snb_composite_backward(const float* raw, const float* z_vals, const float* r
                            float noise_std, int white_back, const float* g_rgb, const float* g_depth,
                            const float* g_weights, int64_t n_rays, int n_samples, float* g_raw, void* stream);
 
+/* ---- training with 16-bit activation storage (round 2) ------------------------------------------------
+ * Same mathematics as snb_field_forward_train / snb_field_backward, but everything the backward streams
+ * per point is stored once, as fp16, in the layout the tensor-core kernels consume directly (32-point tiles
+ * of 16-byte cells, sinnerf_b200/csrc/act16.cuh): 4.5 KB of saved activations per point instead of 8.9 KB,
+ * ~2.5 KB of HBM traffic per point and 256-wide layer in the backward instead of ~5 KB, no conversion /
+ * transposition warps.  Gradients between layers are fp16 x a per-tensor power-of-two scale the kernels
+ * choose on the device from a rigorous growth bound (nothing overflows, no host synchronisation); the
+ * parameter gradients are accumulated in fp32.  Tensor-core precision modes only.
+ *   act16     : one device buffer of snb_act16_bytes(P) bytes, 256-byte aligned (opaque; forward -> backward)
+ *   workspace : one device buffer of snb_bwd16_workspace_bytes(P) bytes, 256-byte aligned
+ *   g_amax    : device word holding the bit pattern of max |g_raw| as snb_composite_backward_loss leaves it,
+ *               or NULL (the library then reduces g_raw itself)                                              */
+size_t snb_act16_bytes(int64_t n_points);
+size_t snb_bwd16_workspace_bytes(int64_t n_points);
+int snb_field_forward_train16(const void* packed, int precision, const float* rays, const float* z_vals,
+                              int64_t n_rays, int n_samples, float* raw, void* act16, void* stream);
+int snb_field_backward16(const float* const* params, float* const* grads, int new_activation, const float* g_raw,
+                         const float* raw, const void* act16, int64_t n_points, void* workspace,
+                         const float* g_amax, void* stream);
+
 /* ---- per-ray losses folded into the compositing ------------------------------------
  * The two losses SinNeRF puts directly on render_rays' outputs (models/sinnerf.py:310-319):
  *   MSELoss  (losses.py:12-22, nn.MSELoss 'mean' on rgb_coarse / rgb_fine)

@@ -3,7 +3,7 @@
 //     "T32" activation layout  [feature/8][32 points][8 features] x 16 bit  that the forward / dgrad
 //     epilogues write: D[m = feature of A][n = feature of B] = sum_p A[p][m] B[p][n]   (the wgrad contraction)
 //       descriptor: LBO = 128 B (next 8 points, K direction), SBO = 512 B (next 8 features, MN direction)
-//   * mixed operand formats in one kind::f16 MMA (A fp16, B bf16)
+//   * mixed operand formats in one kind::f16 MMA (A fp16, B bf16): illegal instruction on sm_100a (SNB_PROBE_MIXED=1)
 //   * SBO = 0 aliasing (all 16 row groups of A read the same 8 features)
 //   * issue-to-completion cycles of MN-major SS MMAs (M128 N256 K16)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o probes/umma_mn_probe probes/umma_mn_probe.cu
@@ -148,12 +148,13 @@ int main() {
   int rc = 0;
   rc |= run(128, 256, 0, 0, 0, "MN-major A,B fp16 x fp16 (T32 layout)");
   rc |= run(128, 256, 1, 1, 0, "MN-major A,B bf16 x bf16");
-  rc |= run(128, 256, 0, 1, 0, "MN-major mixed: A fp16, B bf16");
-  rc |= run(128, 256, 1, 0, 0, "MN-major mixed: A bf16, B fp16");
   rc |= run(128, 128, 0, 0, 0, "MN-major fp16, N=128");
   rc |= run(128, 64, 0, 0, 0, "MN-major fp16, N=64");
   rc |= run(128, 32, 0, 0, 0, "MN-major fp16, N=32");
   rc |= run(8, 256, 0, 0, 1, "A aliased with SBO=0 (8 features x16)");
   printf(rc ? "PROBE FAILED\n" : "PROBE OK\n");
+  // mixed operand formats (A fp16 with B bf16) are NOT accepted by kind::f16 on sm_100a: the launch dies with
+  // "an illegal instruction was encountered" (measured, round 2) -- run last, not part of the verdict
+  if (getenv("SNB_PROBE_MIXED")) run(128, 256, 0, 1, 0, "MN-major mixed: A fp16, B bf16");
   return rc;
 }

@@ -71,6 +71,11 @@ SIGNATURES = {
                                              C.POINTER(SnbLossSpec), c_f, c_f, c_f, c_f, c_f, c_f]),
     "snb_composite_backward_loss": (C.c_int, [c_f, c_f, c_f, c_f, C.c_float, C.c_int, c_f, c_f, c_f,
                                               C.POINTER(SnbLossSpec), c_f, c_f, c_f, C.c_int64, C.c_int, c_f, c_f, c_f]),
+    "snb_act16_bytes": (C.c_size_t, [C.c_int64]),
+    "snb_bwd16_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "snb_field_forward_train16": (C.c_int, [c_f, C.c_int, c_f, c_f, C.c_int64, C.c_int, c_f, c_f, c_f]),
+    "snb_field_backward16": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, c_f, c_f, c_f, C.c_int64,
+                                       c_f, c_f, c_f]),
     "snb_adam_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_f, c_f, C.POINTER(SnbAdamArgs),
                                 C.c_int, C.c_int, c_f, c_f]),
     "snb_field_backward": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, c_f, c_f, c_f, c_f, c_f,

@@ -61,6 +61,11 @@ int field_backward_fp32(const float* const*, float* const*, int, const float*, c
                         uint32_t*, cudaStream_t);
 int launch_generate_rays(const float*, float, float, float, float, float, float, int, int, int, int, int, int, float*,
                          cudaStream_t);
+int field_forward_train16_tc(const void*, int, const float*, const float*, int64_t, int, float*, void*, cudaStream_t);
+size_t act16_bytes(long long);
+size_t bwd16_workspace_bytes(long long);
+int field_backward16(const float* const*, float* const*, int, const float*, const float*, const void*, long long, void*,
+                     const float*, cudaStream_t);
 int adam_step_pack(float* const*, const float* const*, float*, float*, const SnbAdamArgs&, int, int, void*, cudaStream_t);
 // tensor-core modes (field_tc.cu)
 size_t tc_packed_bytes(int precision);
@@ -301,6 +306,37 @@ int snb_field_backward(const float* const* params, float* const* grads, int new_
               "snb_field_backward: null pointer");
   return field_backward_fp32(params, grads, new_activation, g_raw, raw, save_enc, save_dir, save_h, save_g,
                              n_points, ws_a, ws_b, ws_s, ws_w, ws_m, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t snb_act16_bytes(int64_t n_points) { return n_points < 0 ? 0 : act16_bytes(n_points); }
+size_t snb_bwd16_workspace_bytes(int64_t n_points) { return n_points < 0 ? 0 : bwd16_workspace_bytes(n_points); }
+
+int snb_field_forward_train16(const void* packed, int precision, const float* rays, const float* z_vals, int64_t n_rays,
+                              int n_samples, float* raw, void* act16, void* stream) {
+  if (int rc = check_precision(precision)) return rc;
+  if (precision == SNB_PREC_FP32)
+    return fail(SNB_ERR_UNSUPPORTED, "snb_field_forward_train16: 16-bit activation storage needs a tensor-core precision mode");
+  SNB_REQUIRE(n_rays >= 0 && n_samples >= 1, "snb_field_forward_train16: bad extents");
+  SNB_REQUIRE(n_rays == 0 || (packed && rays && z_vals && raw && act16), "snb_field_forward_train16: null pointer");
+  SNB_REQUIRE(aligned16(rays) && aligned16(raw) && (reinterpret_cast<uintptr_t>(act16) & 255u) == 0,
+              "snb_field_forward_train16: rays / raw must be 16-byte and act16 256-byte aligned");
+  return field_forward_train16_tc(packed, precision, rays, z_vals, n_rays, n_samples, raw, act16,
+                                  reinterpret_cast<cudaStream_t>(stream));
+}
+
+int snb_field_backward16(const float* const* params, float* const* grads, int new_activation, const float* g_raw,
+                         const float* raw, const void* act16, int64_t n_points, void* workspace, const float* g_amax,
+                         void* stream) {
+  SNB_REQUIRE(n_points >= 0, "snb_field_backward16: negative point count");
+  SNB_REQUIRE(params && grads, "snb_field_backward16: null parameter arrays");
+  for (int i = 0; i < SNB_N_PARAM_TENSORS; ++i)
+    SNB_REQUIRE(params[i] && grads[i], "snb_field_backward16: parameter / gradient tensor %d is null", i);
+  SNB_REQUIRE(n_points == 0 || (g_raw && raw && act16 && workspace), "snb_field_backward16: null pointer");
+  SNB_REQUIRE(aligned16(g_raw) && aligned16(raw) && (reinterpret_cast<uintptr_t>(act16) & 255u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+              "snb_field_backward16: g_raw / raw must be 16-byte, act16 / workspace 256-byte aligned");
+  return field_backward16(params, grads, new_activation, g_raw, raw, act16, n_points, workspace, g_amax,
+                          reinterpret_cast<cudaStream_t>(stream));
 }
 
 int snb_adam_step(float* const* params, const float* const* grads, float* exp_avg, float* exp_avg_sq,

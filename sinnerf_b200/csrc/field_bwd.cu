@@ -423,6 +423,17 @@ __global__ void unfold_grads_kernel(const float* __restrict__ Wd, const float* _
   }
 }
 
+// launch wrappers shared with the 16-bit backward (bwd16.cu)
+int launch_fold_weights(const float* Wd, const float* Wf, float* ws, cudaStream_t st) {
+  fold_weights_kernel<<<128, 256, 0, st>>>(Wd, Wf, ws);
+  return check_launch("fold_weights_kernel");
+}
+int launch_unfold_grads(const float* Wd, const float* Wf, const float* bf, const float* ws, float* dWd, float* dbd,
+                        float* dWf, float* dbf, cudaStream_t st) {
+  unfold_grads_kernel<<<392, 256, 0, st>>>(Wd, Wf, bf, ws, dWd, dbd, dWf, dbf);
+  return check_launch("unfold_grads_kernel");
+}
+
 int field_backward_fp32(const float* const* params, float* const* grads, int new_activation, const float* g_raw,
                         const float* raw, const float* save_enc, const float* save_dir, const float* save_h,
                         const float* save_g, int64_t n_points, float* ws_a, float* ws_b, float* ws_s, float* ws_w,

@@ -54,6 +54,7 @@
 #include <type_traits>
 #include <utility>
 
+#include "act16.cuh"
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -431,12 +432,14 @@ int launch_pack_tc(const float* const* params, int precision, int new_activation
 }
 
 // ------------------------------------------------------------------ shared memory
-template <bool kSplit, int kCg, bool kTrain = false>
+// kTrain: 0 = inference, 1 = training forward keeping fp32 row-major activations (snb_field_forward_train),
+//         2 = training forward keeping fp16 activations in the T32 layout + ReLU mask words (act16.cuh)
+template <bool kSplit, int kCg, int kTrain = 0>
 struct TcSmem {
   static constexpr int kParts = kSplit ? 2 : 1;
   static constexpr uint32_t kStageBytes = Geo<kCg>::kPartBytesMax * kParts;   // this CTA's share of a full chunk
   // up to 160 KB of weights in flight; the training forward gives 64 KB of that to the store tiles below
-  static constexpr int kStagesRaw = ((kTrain ? 96 : 160) * 1024) / kStageBytes;
+  static constexpr int kStagesRaw = ((kTrain == 1 ? 96 : 160) * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
   alignas(1024) unsigned char ring[kStages][kStageBytes];
   alignas(128) unsigned char enc[kParts][kTile * kXyzPad * 2];   // canonical [k8][row][8] hi (, lo)
@@ -447,7 +450,7 @@ struct TcSmem {
   // training forward: per-warp 32 x 16 transposition tiles (row stride 20 words: conflict-free 128-bit
   // accesses) so the activations leave as 64 contiguous bytes per 4 lanes instead of 16 bytes per lane
   // at a 1 KB stride -- 8 lines per store instruction instead of 32
-  alignas(16) float store_tile[kTrain ? kEpiWarps : 1][kTrain ? 32 : 1][20];
+  alignas(16) float store_tile[kTrain == 1 ? kEpiWarps : 1][kTrain == 1 ? 32 : 1][20];
   uint64_t full[16], empty[16];
   uint64_t d_full[2], a_ready[4], a_free, enc_ready, dir_ready, d_drained;
   uint32_t tmem_base;
@@ -468,6 +471,13 @@ struct TcParams {
   float* save_dir;         // (P,32)
   float* save_h;           // (8,P,256)
   float* save_g;           // (P,128)
+  // training forward, 16-bit storage (kTrain == 2): sections of the act16 buffer (act16.cuh)
+  unsigned char* a_enc;    // (Ppad,64)  fp16 T32
+  unsigned char* a_dir;    // (Ppad,32)
+  unsigned char* a_h;      // 8 x (Ppad,256)
+  unsigned char* a_g;      // (Ppad,128)
+  uint32_t* a_mask;        // (8, 8, Ppad)
+  long long ppad;
   int debug;   // timing experiments only (SNB_TC_DEBUG): 2 = epilogue skips math, 4 = no MMAs
 };
 
@@ -481,9 +491,9 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;"
 // canonical (SWIZZLE_NONE, K-major) byte offset of element (row, k) in a [k8][128 rows][8] block
 __device__ __forceinline__ uint32_t canon_off(int row, int k) { return (uint32_t)(k >> 3) * (kTile * 16) + row * 16 + (k & 7) * 2; }
 
-template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, bool kTrain = false>
+template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, int kTrain = 0>
 __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
-  static_assert(!(kTrain && kEmbedded), "the training forward is the fused (rays, z) entry only");
+  static_assert(!(kTrain != 0 && kEmbedded), "the training forward is the fused (rays, z) entry only");
   using Smem = TcSmem<kSplit, kCg, kTrain>;
   using G = Geo<kCg>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -694,7 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     // training forward: 16 consecutive columns of this warp's 32 rows -> global, through the warp's tile.
     // `x4[k]` = this thread's row, columns [4k, 4k+4); dst_block = address of (first row of the block, first column)
     auto store_block16 = [&](const float4 (&x4)[4], float* dst_block, long long ld, long long pt_block0) {
-      float (*tile)[20] = s.store_tile[kTrain ? warp : 0];
+      float (*tile)[20] = s.store_tile[kTrain == 1 ? warp : 0];
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(&tile[lane][4 * k]) = x4[k];
@@ -705,6 +715,17 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
         if (pt_block0 + r < p.n_points)
           *reinterpret_cast<float4*>(dst_block + r * ld + 4 * c) = *reinterpret_cast<const float4*>(&tile[r][4 * c]);
       }
+    };
+
+    // 16-bit storage: 8 consecutive features of this thread's point -> one 16-byte cell of a T32 tensor; the 32
+    // lanes of the warp are 32 consecutive points, so a store instruction covers 512 contiguous bytes
+    auto store_cell16 = [&](unsigned char* base, long long pt, int f8, int F, const float (&v)[8]) {
+      if (pt >= p.ppad) return;
+      const bool live = pt < p.n_points;
+      uint4 c;
+      c.x = live ? pack_half2_sat(v[0], v[1]) : 0u; c.y = live ? pack_half2_sat(v[2], v[3]) : 0u;
+      c.z = live ? pack_half2_sat(v[4], v[5]) : 0u; c.w = live ? pack_half2_sat(v[6], v[7]) : 0u;
+      *reinterpret_cast<uint4*>(base + a16_cell(pt, f8, F)) = c;
     };
 
     // ---- positional encodings of one tile -> smem (canonical, hi/lo).  Split in pieces so they
@@ -765,10 +786,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           x[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, zz));
         }
         embed8(x, c_lo, kXyzCh, SNB_XYZ_FREQS, v);
-        if (kTrain && pt < p.n_points) {
+        if (kTrain == 1 && pt < p.n_points) {
           float4* dst = reinterpret_cast<float4*>(p.save_enc + pt * kXyzPad + c_lo);
           dst[0] = make_float4(v[0], v[1], v[2], v[3]); dst[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
+        if (kTrain == 2) store_cell16(p.a_enc, pt, c_lo >> 3, kXyzPad, v);
       }
       put8(s.enc[0], s.enc[kSplit ? 1 : 0], c_lo / 8, v);
       if (part == 1) {
@@ -793,10 +815,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           d[0] = p.rays[ray * 8 + 3]; d[1] = p.rays[ray * 8 + 4]; d[2] = p.rays[ray * 8 + 5];
         }
         embed8(d, c_lo, kDirCh, SNB_DIR_FREQS, v);
-        if (kTrain && pt < p.n_points) {
+        if (kTrain == 1 && pt < p.n_points) {
           float4* dst = reinterpret_cast<float4*>(p.save_dir + pt * kDirPad + c_lo);
           dst[0] = make_float4(v[0], v[1], v[2], v[3]); dst[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
+        if (kTrain == 2) store_cell16(p.a_dir, pt, c_lo >> 3, kDirPad, v);
       }
       put8(s.dir[0], s.dir[kSplit ? 1 : 0], c_lo / 8, v);
       fence_proxy_async_smem();
@@ -837,12 +860,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
             const float2* b2 = reinterpret_cast<const float2*>(bias + c0);
             const float2* w2 = reinterpret_cast<const float2*>(s.cst + CL.sigma_w + c0);
             const long long pt_block0 = pt - lane;      // first row of this warp's 32-row block
-            float* save_blk = kTrain ? p.save_h + ((size_t)l * p.n_points + pt_block0) * kWidth + c0 : nullptr;
+            float* save_blk = kTrain == 1 ? p.save_h + ((size_t)l * p.n_points + pt_block0) * kWidth + c0 : nullptr;
             float4 keep[4];
+            uint32_t h16[kTrain == 2 ? 16 : 1];      // this thread's 32 post-ReLU values as fp16 pairs
+            uint32_t mword = 0;                      // [value > 0] of the 32 columns (the fp32 test the reference's ReLU makes)
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               float x[4];
-              if (kRelu && !kSigma && !kTrain) {
+              if (kRelu && !kSigma && kTrain == 0) {
                 // nobody needs the fp32 post-activation value: ReLU and the fp16 range guard ride on the converts
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -863,12 +888,28 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
                   sig_part = fmaf(x[2 * e], ww.x, sig_part); sig_part = fmaf(x[2 * e + 1], ww.y, sig_part);
                 }
               }
-              if (kTrain) {
+              if (kTrain == 1) {
                 keep[(j >> 1) & 3] = make_float4(x[0], x[1], x[2], x[3]);
                 if (((j >> 1) & 3) == 3) store_block16(keep, save_blk + (j >> 3) * 16, kWidth, pt_block0);
               }
               split_pair<kBf16, kSplit, kRelu>(x[0], x[1], v[2 * j], v[2 * j + 1]);
               split_pair<kBf16, kSplit, kRelu>(x[2], x[3], v[2 * j + 2], v[2 * j + 3]);
+              if (kTrain == 2) {
+                // fp16 modes: the hi word of the split IS rn_fp16(value) (saturated); bf16 modes convert separately
+                h16[j] = kBf16 ? pack_half2_sat(x[0], x[1]) : v[2 * j];
+                h16[j + 1] = kBf16 ? pack_half2_sat(x[2], x[3]) : v[2 * j + 2];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) mword |= (x[e] > 0.f ? 1u : 0u) << (2 * j + e);
+              }
+            }
+            if (kTrain == 2 && pt < p.ppad) {
+              const bool live = pt < p.n_points;
+              unsigned char* hb = p.a_h + (size_t)l * (size_t)p.ppad * (kWidth * 2);
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(hb + a16_cell(pt, (c0 >> 3) + c, kWidth)) =
+                    live ? make_uint4(h16[4 * c], h16[4 * c + 1], h16[4 * c + 2], h16[4 * c + 3]) : make_uint4(0u, 0u, 0u, 0u);
+              p.a_mask[a16_mask_index(l, c0 >> 5, pt, p.ppad)] = live ? mword : 0u;
             }
           };
           if (l == 7) finish_group(std::true_type{}, std::true_type{});
@@ -924,6 +965,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
         tc_fence_before();
         signal(&s.d_drained);      // D[0,128) is in registers: the next slot's layer 1 may overwrite it
         trace(tr, tb + 2);
+        uint32_t g16[kTrain == 2 ? 16 : 1];        // this thread's 32 direction-layer outputs as fp16 pairs
         {
           const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
           const float4* w0 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + c0);
@@ -944,14 +986,22 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
             }
-            if (kTrain) {
+            if (kTrain == 1) {
               keep[j4 & 3] = make_float4(x[0], x[1], x[2], x[3]);
               if ((j4 & 3) == 3) store_block16(keep, p.save_g + (pt - lane) * kHalf + c0 + (j4 >> 2) * 16, kHalf, pt - lane);
             }
+            if (kTrain == 2) { g16[2 * j4] = pack_half2_sat(x[0], x[1]); g16[2 * j4 + 1] = pack_half2_sat(x[2], x[3]); }
             a0 = fmaf(x[0], r0.x, a0); a0 = fmaf(x[1], r0.y, a0); a0 = fmaf(x[2], r0.z, a0); a0 = fmaf(x[3], r0.w, a0);
             a1 = fmaf(x[0], r1.x, a1); a1 = fmaf(x[1], r1.y, a1); a1 = fmaf(x[2], r1.z, a1); a1 = fmaf(x[3], r1.w, a1);
             a2 = fmaf(x[0], r2.x, a2); a2 = fmaf(x[1], r2.y, a2); a2 = fmaf(x[2], r2.z, a2); a2 = fmaf(x[3], r2.w, a2);
           }
+        }
+        if (kTrain == 2 && pt < p.ppad) {
+          const bool live = pt < p.n_points;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(p.a_g + a16_cell(pt, (c0 >> 3) + c, kHalf)) =
+                live ? make_uint4(g16[4 * c], g16[4 * c + 1], g16[4 * c + 2], g16[4 * c + 3]) : make_uint4(0u, 0u, 0u, 0u);
         }
         trace(tr, tb + 3);
         // rgb partial sums go through the dir-embedding buffer: its last readers (this slot's dir-layer
@@ -981,7 +1031,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 }
 
 // ------------------------------------------------------------------ host
-template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, bool kTrain = false>
+template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, int kTrain = 0>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
   static SmemOptIn optin;
   const long long ntiles = (p.n_points + kTile - 1) / kTile;
@@ -1048,9 +1098,30 @@ int field_forward_train_tc(const void* packed, int precision, const float* rays,
   p.out = raw;
   p.save_enc = save_enc; p.save_dir = save_dir; p.save_h = save_h; p.save_g = save_g;
   switch (precision) {
-    case SNB_PREC_F16X3: return launch_tc<false, true, false, 2, true>(p, st);
-    case SNB_PREC_BF16X3: return launch_tc<true, true, false, 2, true>(p, st);
-    case SNB_PREC_BF16: return launch_tc<true, false, false, 2, true>(p, st);
+    case SNB_PREC_F16X3: return launch_tc<false, true, false, 2, 1>(p, st);
+    case SNB_PREC_BF16X3: return launch_tc<true, true, false, 2, 1>(p, st);
+    case SNB_PREC_BF16: return launch_tc<true, false, false, 2, 1>(p, st);
+  }
+  return fail(SNB_ERR_INVALID, "precision %d is not a tensor-core mode", precision);
+}
+
+// training forward with 16-bit activation storage (act16.cuh): `act16` = one buffer of make_act16_layout(P).total bytes
+int field_forward_train16_tc(const void* packed, int precision, const float* rays, const float* z, int64_t n_rays,
+                             int n_samples, float* raw, void* act16, cudaStream_t st) {
+  TcParams p{};
+  p.image = reinterpret_cast<const unsigned char*>(packed);
+  p.rays = rays; p.z = z; p.n_samples = n_samples;
+  p.n_points = (long long)n_rays * n_samples;
+  p.out = raw;
+  const Act16Layout L = make_act16_layout(p.n_points);
+  unsigned char* b = reinterpret_cast<unsigned char*>(act16);
+  p.a_enc = b + L.enc; p.a_dir = b + L.dir; p.a_h = b + L.h[0]; p.a_g = b + L.g;
+  p.a_mask = reinterpret_cast<uint32_t*>(b + L.mask);
+  p.ppad = a16_pad(p.n_points);
+  switch (precision) {
+    case SNB_PREC_F16X3: return launch_tc<false, true, false, 2, 2>(p, st);
+    case SNB_PREC_BF16X3: return launch_tc<true, true, false, 2, 2>(p, st);
+    case SNB_PREC_BF16: return launch_tc<true, false, false, 2, 2>(p, st);
   }
   return fail(SNB_ERR_INVALID, "precision %d is not a tensor-core mode", precision);
 }

@@ -117,19 +117,30 @@ class _RenderPass(torch.autograd.Function):
         P = n * S
         img = model.packed_weights(prec)
         raw = torch.empty(n, S, 4, device=dev, dtype=torch.float32)
-        save_enc = torch.empty(P, 64, device=dev, dtype=torch.float32)
-        save_dir = torch.empty(P, 32, device=dev, dtype=torch.float32)
-        save_h = torch.empty(8, P, 256, device=dev, dtype=torch.float32)
-        save_g = torch.empty(P, 128, device=dev, dtype=torch.float32)
+        store16 = prec != _lib.PRECISIONS["fp32"] and config.get_train_storage() == "fp16"
+        if store16:
+            # one fp16 copy of everything the backward streams, in the MMA-ready tile layout (csrc/act16.cuh)
+            act16 = torch.empty(lib.snb_act16_bytes(P), device=dev, dtype=torch.uint8)
+            save_enc = save_dir = save_h = save_g = raw.new_empty(0)
+        else:
+            act16 = raw.new_empty(0)
+            save_enc = torch.empty(P, 64, device=dev, dtype=torch.float32)
+            save_dir = torch.empty(P, 32, device=dev, dtype=torch.float32)
+            save_h = torch.empty(8, P, 256, device=dev, dtype=torch.float32)
+            save_g = torch.empty(P, 128, device=dev, dtype=torch.float32)
         rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
         depth = torch.empty(n, device=dev, dtype=torch.float32)
         w = torch.empty(n, S, device=dev, dtype=torch.float32)
         loss = torch.zeros(2, device=dev, dtype=torch.float32) if spec is None else torch.empty(2, device=dev)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            _lib.check(lib.snb_field_forward_train(_lib.ptr(img), prec, _lib.ptr(rays), _lib.ptr(z), n, S, _lib.ptr(raw),
-                                                   _lib.ptr(save_enc), _lib.ptr(save_dir), _lib.ptr(save_h),
-                                                   _lib.ptr(save_g), st), "snb_field_forward_train")
+            if store16:
+                _lib.check(lib.snb_field_forward_train16(_lib.ptr(img), prec, _lib.ptr(rays), _lib.ptr(z), n, S,
+                                                         _lib.ptr(raw), _lib.ptr(act16), st), "snb_field_forward_train16")
+            else:
+                _lib.check(lib.snb_field_forward_train(_lib.ptr(img), prec, _lib.ptr(rays), _lib.ptr(z), n, S, _lib.ptr(raw),
+                                                       _lib.ptr(save_enc), _lib.ptr(save_dir), _lib.ptr(save_h),
+                                                       _lib.ptr(save_g), st), "snb_field_forward_train")
             if spec is None:
                 _lib.check(lib.snb_composite_forward(_lib.ptr(raw), 4, _lib.ptr(z), _lib.ptr(rays), _lib.ptr(noise),
                                                      noise_std, int(white_back), n, S, _lib.ptr(rgb), _lib.ptr(depth),
@@ -141,8 +152,8 @@ class _RenderPass(torch.autograd.Function):
                                                           _lib.ptr(depth), _lib.ptr(w), _lib.ptr(loss),
                                                           _lib.ptr(_loss_workspace(dev)), st), "snb_composite_forward_loss")
         ctx.save_for_backward(raw, z, rays, noise if noise is not None else raw.new_empty(0), rgb, depth,
-                              save_enc, save_dir, save_h, save_g, *params)
-        ctx.cfg = (float(noise_std), int(white_back), noise is not None, int(model.use_new_activation))
+                              save_enc, save_dir, save_h, save_g, act16, *params)
+        ctx.cfg = (float(noise_std), int(white_back), noise is not None, int(model.use_new_activation), store16)
         ctx.spec = spec          # plain (non-differentiable) tensors + floats
         if spec is None:
             ctx.mark_non_differentiable(loss)
@@ -151,8 +162,8 @@ class _RenderPass(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_w, g_loss):
         lib = _lib.load()
-        raw, z, rays, noise, rgb, depth, save_enc, save_dir, save_h, save_g, *params = ctx.saved_tensors
-        noise_std, white_back, has_noise, new_activation = ctx.cfg
+        raw, z, rays, noise, rgb, depth, save_enc, save_dir, save_h, save_g, act16, *params = ctx.saved_tensors
+        noise_std, white_back, has_noise, new_activation, store16 = ctx.cfg
         dev = raw.device
         n, S = z.shape
         P = n * S
@@ -171,25 +182,31 @@ class _RenderPass(torch.autograd.Function):
             total += (p.numel() + 3) // 4 * 4
         flat = torch.zeros(total, device=dev, dtype=torch.float32)
         grads = [flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, ps)]
-        ws_a = torch.empty(P, 256, device=dev, dtype=torch.float32)
-        ws_b = torch.empty(P, 256, device=dev, dtype=torch.float32)
-        ws_s = torch.empty(P, 128, device=dev, dtype=torch.float32)
-        ws_w = torch.empty(_lib.BWD_WS_FLOATS, device=dev, dtype=torch.float32)
-        ws_m = torch.empty(P, 8, device=dev, dtype=torch.int32)
         parr = (C.c_void_p * 24)(*[p.data_ptr() for p in ps])
         garr = (C.c_void_p * 24)(*[g.data_ptr() for g in grads])
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
+            g_amax = torch.zeros(1, device=dev, dtype=torch.float32) if store16 else None     # bit pattern of max |g_raw|
             _lib.check(lib.snb_composite_backward_loss(_lib.ptr(raw), _lib.ptr(z), _lib.ptr(rays),
                                                        _lib.ptr(noise) if has_noise else None, noise_std, white_back,
                                                        _lib.ptr(keep[0]), _lib.ptr(keep[1]), _lib.ptr(keep[2]),
                                                        C.byref(ls) if ls is not None else None, _lib.ptr(rgb),
-                                                       _lib.ptr(depth), _lib.ptr(gl), n, S, _lib.ptr(g_raw), None, st),
+                                                       _lib.ptr(depth), _lib.ptr(gl), n, S, _lib.ptr(g_raw), _lib.ptr(g_amax), st),
                        "snb_composite_backward_loss")
-            _lib.check(lib.snb_field_backward(parr, garr, new_activation, _lib.ptr(g_raw), _lib.ptr(raw),
-                                              _lib.ptr(save_enc), _lib.ptr(save_dir), _lib.ptr(save_h),
-                                              _lib.ptr(save_g), P, _lib.ptr(ws_a), _lib.ptr(ws_b), _lib.ptr(ws_s),
-                                              _lib.ptr(ws_w), _lib.ptr(ws_m), st), "snb_field_backward")
+            if store16:
+                ws = torch.empty(lib.snb_bwd16_workspace_bytes(P), device=dev, dtype=torch.uint8)
+                _lib.check(lib.snb_field_backward16(parr, garr, new_activation, _lib.ptr(g_raw), _lib.ptr(raw), _lib.ptr(act16),
+                                                    P, _lib.ptr(ws), _lib.ptr(g_amax), st), "snb_field_backward16")
+            else:
+                ws_a = torch.empty(P, 256, device=dev, dtype=torch.float32)
+                ws_b = torch.empty(P, 256, device=dev, dtype=torch.float32)
+                ws_s = torch.empty(P, 128, device=dev, dtype=torch.float32)
+                ws_w = torch.empty(_lib.BWD_WS_FLOATS, device=dev, dtype=torch.float32)
+                ws_m = torch.empty(P, 8, device=dev, dtype=torch.int32)
+                _lib.check(lib.snb_field_backward(parr, garr, new_activation, _lib.ptr(g_raw), _lib.ptr(raw),
+                                                  _lib.ptr(save_enc), _lib.ptr(save_dir), _lib.ptr(save_h),
+                                                  _lib.ptr(save_g), P, _lib.ptr(ws_a), _lib.ptr(ws_b), _lib.ptr(ws_s),
+                                                  _lib.ptr(ws_w), _lib.ptr(ws_m), st), "snb_field_backward")
         return (None, None, None, None, None, None, None, None, *grads)
 
 

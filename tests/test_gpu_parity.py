@@ -107,13 +107,15 @@ def test_mlp_forward_matches_golden(tag, params):
     for mode in available_modes():
         sinnerf_b200.set_precision(mode)
         try:
-            out = m(x).cpu()
+            with torch.no_grad():       # module forward = inference kernels; it refuses to run under autograd
+                out = m(x).cpu()
             tol = 1e-4 if mode != "bf16" else 3e-2
             if mode == "bf16x3":
                 tol = 3e-4
             assert_close(out, ST[f"mlp_{tag}_out"], tol, f"{mode}:{tag}")
             if tag == "seed0":
-                s = m(x[:, :63].contiguous(), sigma_only=True).cpu()
+                with torch.no_grad():
+                    s = m(x[:, :63].contiguous(), sigma_only=True).cpu()
                 assert_close(s, ST["mlp_seed0_sigma"], tol, f"{mode}:sigma_only")
         finally:
             sinnerf_b200.set_precision(before)
@@ -132,7 +134,8 @@ def test_mlp_old_activation():
     try:
         for mode in fp32_class_modes():
             sinnerf_b200.set_precision(mode)
-            out = m(x.to(DEV)).cpu()
+            with torch.no_grad():
+                out = m(x.to(DEV)).cpu()
             assert_close(out, ref, 1e-4, f"relu/sigmoid variant ({mode})")
     finally:
         sinnerf_b200.set_precision(before)
