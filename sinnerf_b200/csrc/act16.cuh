@@ -25,8 +25,11 @@
 // gradients are stored as fp16 x 2^k with a per-tensor power-of-two scale chosen ON THE DEVICE from a
 // rigorous bound (measured max |dY| of the previous layer x max column L1 norm of the weights), so nothing
 // overflows and the top of the range is used; wgrad divides the scale out of its fp32 accumulators.
-// Weights enter dgrad as fp16 hi + lo (2 products).  Measured effect on the parameter gradients:
-// tests/test_gpu_backward.py (<= 1e-3 per tensor vs autograd through the fp32 oracle).
+// The layer-to-layer gradient chain carries a second fp16 plane with the rounding residual (hi + lo = 22
+// bits; dgrad16.cu), so the only 11-bit roundings a weight gradient sees are ONE of its layer's gradient
+// and ONE of its layer's input.  Weights enter dgrad as fp16 hi + lo.  Measured effect on the parameter
+// gradients: tests/test_gpu_round2.py, tests/test_gpu_backward.py (<= 1e-3 per tensor vs autograd through
+// the fp32 oracle).
 #pragma once
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -64,11 +67,12 @@ __host__ __device__ __forceinline__ size_t a16_mask_index(int l, int w, long lon
 }
 
 // ---- workspace of one backward pass (snb_field_backward16)
-//   dS (Ppad,128) | hg (Ppad,8) | dYa (Ppad,256) | dYb (Ppad,256)   fp16 T32
+//   dS (Ppad,128) | hg (Ppad,8) | dYa (Ppad,256) | dYb (Ppad,256)   fp16 T32, hi planes
+//   dS_lo | dYa_lo | dYb_lo                                            residual planes of the gradient chain
 //   fold (SNB_BWD_WS_FLOATS floats) | state (kBwdStateFloats floats)
 constexpr int kBwdStateFloats = 64;
 struct Bwd16Layout {
-  size_t ds, hg, dya, dyb, fold, state, total;
+  size_t ds, hg, dya, dyb, ds_lo, dya_lo, dyb_lo, fold, state, total;
 };
 __host__ __device__ inline Bwd16Layout make_bwd16_layout(long long n_points) {
   const size_t pp = (size_t)a16_pad(n_points);
@@ -78,6 +82,9 @@ __host__ __device__ inline Bwd16Layout make_bwd16_layout(long long n_points) {
   L.hg = off; off += pp * 8 * 2;
   L.dya = off; off += pp * 256 * 2;
   L.dyb = off; off += pp * 256 * 2;
+  L.ds_lo = off; off += pp * 128 * 2;
+  L.dya_lo = off; off += pp * 256 * 2;
+  L.dyb_lo = off; off += pp * 256 * 2;
   L.fold = off; off += (size_t)(2 * 128 * 256 + 128) * 4;
   L.state = off; off += (size_t)kBwdStateFloats * 4;
   L.total = (off + 255) & ~(size_t)255;

@@ -7,12 +7,14 @@
 //   prepare   : zero the running maxima, W' = Wd[:, :256] Wf, max column L1 norms of every weight matrix a
 //               dgrad multiplies by (the growth bound behind each layer's power-of-two gradient scale)
 //   heads     : rgb head + its activation, direction-layer activation -> dS (fp16 T32, scaled), the head-gradient
-//               cells hg = [g_pre_rgb(3), g_sigma] (fp16 T32, scaled), db_rgb, db_sigma            (head_bwd16_kernel)
+//               cells hg = [g_pre_rgb(3), g_sigma | their fp16 rounding residuals] (fp16 T32, scaled), db_rgb, db_sigma
+//                                                                                                    (head_bwd16_kernel)
 //   dir layer : dW', db' = wgrad16(dS, h8) with the sigma-head rows riding on the same X operand (dW_sigma = hg[3]^T h8);
 //               dWd[:, 256:] = wgrad16(dS, dir);  dW_rgb = hg[0..2]^T g;  unfold through W'
 //   layers    : dH_{l-1} = dgrad16(dH_l, W_l) * mask(h_l);  dW_l, db_l = wgrad16(dH_l, h_l)          l = 8 .. 1
 // HBM per point: ~2.5 KB per 256-wide layer (fp32 version: ~5 KB), 4.5 KB of saved activations (8.9 KB).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "act16.cuh"
 #include "common.cuh"
@@ -27,9 +29,9 @@ int launch_unfold_grads(const float* Wd, const float* Wf, const float* bf, const
 int run_wgrad16(const void* dY, int FA, const void* X, int FB, int K, float* dW, int ldw, int col_off, float* db,
                 const float* scale, const void* hg, float* const* dH, const float* scale2, long long n_points_pad,
                 cudaStream_t st);
-int run_dgrad16(const void* dY, int N, const float* W, int ldw, int col_off, const uint32_t* mask, const float* extra,
-                int extra_stride, const float* evec, void* dX, float* state, int st_amax_in, int st_scale_in, int st_l1,
-                int st_amax_out, int st_scale_out, long long P, cudaStream_t st);
+int run_dgrad16(const void* dY, const void* dY_lo, int N, const float* W, int ldw, int col_off, const uint32_t* mask,
+                const float* extra, int extra_stride, const float* evec, void* dX, void* dX_lo, float* state, int st_amax_in,
+                int st_scale_in, int st_l1, int st_amax_out, int st_scale_out, long long P, cudaStream_t st);
 
 namespace {
 
@@ -101,6 +103,7 @@ struct Head16Args {
   const float* Wr;           // (3,128)
   int new_activation;
   unsigned char* dS;         // (Ppad,128) fp16 T32, scaled by state[ST_SCALE_DS]
+  unsigned char* dS_lo;      // residual plane (nullable)
   unsigned char* hg;         // (Ppad,8) fp16 T32, scaled by state[ST_SCALE_HG]
   float* dbr; float* dbs;
   float* state;
@@ -140,13 +143,20 @@ __global__ void __launch_bounds__(256) head_bwd16_kernel(Head16Args a) {
       gs = g.w;
       abr0 += gp[0]; abr1 += gp[1]; abr2 += gp[2]; abs_ += gs;
     }
-    *reinterpret_cast<uint4*>(a.hg + a16_cell(p, 0, 8)) =
-        make_uint4(pack_half2_sat(gp[0] * s_hg, gp[1] * s_hg), pack_half2_sat(gp[2] * s_hg, gs * s_hg), 0u, 0u);
+    {
+      // head-gradient cell: features 0..3 = fp16 hi of [g_pre_rgb(3), g_sigma] * s_hg, features 4..7 = the rounding
+      // residuals (the cell has the room): the head rows of wgrad16 add rows r and r + 4, i.e. 22-bit head gradients
+      const float hv[4] = {gp[0] * s_hg, gp[1] * s_hg, gp[2] * s_hg, gs * s_hg};
+      const uint32_t h01 = pack_half2_sat(hv[0], hv[1]), h23 = pack_half2_sat(hv[2], hv[3]);
+      const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01)), f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+      *reinterpret_cast<uint4*>(a.hg + a16_cell(p, 0, 8)) =
+          make_uint4(h01, h23, pack_half2_sat(hv[0] - f01.x, hv[1] - f01.y), pack_half2_sat(hv[2] - f23.x, hv[3] - f23.y));
+    }
 #pragma unroll 4
     for (int f8 = 0; f8 < 16; ++f8) {
       const uint4 c = live ? __ldg(reinterpret_cast<const uint4*>(a.G + a16_cell(p, f8, kHalf))) : make_uint4(0u, 0u, 0u, 0u);
       const uint32_t w[4] = {c.x, c.y, c.z, c.w};
-      uint32_t o[4];
+      uint32_t o[4], ol[4];
 #pragma unroll
       for (int j2 = 0; j2 < 4; ++j2) {
         const float2 gg = __half22float2(*reinterpret_cast<const __half2*>(&w[j2]));
@@ -162,8 +172,11 @@ __global__ void __launch_bounds__(256) head_bwd16_kernel(Head16Args a) {
           amax = fmaxf(amax, fabsf(ds[e]));
         }
         o[j2] = pack_half2_sat(ds[0], ds[1]);
+        const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(&o[j2]));
+        ol[j2] = pack_half2_sat(ds[0] - hv.x, ds[1] - hv.y);
       }
       *reinterpret_cast<uint4*>(a.dS + a16_cell(p, f8, kHalf)) = make_uint4(o[0], o[1], o[2], o[3]);
+      if (a.dS_lo != nullptr) *reinterpret_cast<uint4*>(a.dS_lo + a16_cell(p, f8, kHalf)) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
     }
   }
 #pragma unroll
@@ -198,6 +211,8 @@ int field_backward16(const float* const* params, float* const* grads, int new_ac
   const uint32_t* mask = reinterpret_cast<const uint32_t*>(act + A.mask);
   auto H = [&](int l) { return act + A.h[l]; };                          // l = 0..7: h1..h8
   auto M = [&](int l) { return mask + (size_t)l * 8 * (size_t)ppad; };   // ReLU mask of h_{l+1}
+  // SNB_BWD16_LO=0: hi-only gradient chain (2.5 KB per point and layer instead of 3; first-layer gradients ~1e-3)
+  static const bool use_lo = !(getenv("SNB_BWD16_LO") && atoi(getenv("SNB_BWD16_LO")) == 0);
   int rc;
   if (cudaMemsetAsync(state, 0, kBwdStateFloats * sizeof(float), st) != cudaSuccess)
     return fail(SNB_ERR_CUDA, "field_backward16: cudaMemsetAsync failed");
@@ -220,7 +235,7 @@ int field_backward16(const float* const* params, float* const* grads, int new_ac
   }
   {
     Head16Args a{reinterpret_cast<const float4*>(g_raw), reinterpret_cast<const float4*>(raw), act + A.g, params[kRgbW],
-                 new_activation, w + B.ds, w + B.hg, grads[kRgbB], grads[kSigmaB], state, P, ppad};
+                 new_activation, w + B.ds, use_lo ? w + B.ds_lo : nullptr, w + B.hg, grads[kRgbB], grads[kSigmaB], state, P, ppad};
     long long tiles = ppad / 32, blocks = (tiles + 7) / 8;
     if (blocks > sm_count() * 4) blocks = sm_count() * 4;
     head_bwd16_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
@@ -244,8 +259,10 @@ int field_backward16(const float* const* params, float* const* grads, int new_ac
   // into h8: through W', plus the sigma head's term; ReLU mask of h8
   unsigned char* cur = w + B.dya;
   unsigned char* nxt = w + B.dyb;
-  if ((rc = run_dgrad16(w + B.ds, 128, fold + kFoldW, 256, 0, M(7), g_raw + 3, 4, params[kSigmaW], cur, state, ST_AMAX_DS,
-                        ST_SCALE_DS, ST_L1_FOLD, ST_AMAX_H0 + 7, ST_SCALE_H0 + 7, P, st)))
+  unsigned char* cur_lo = use_lo ? w + B.dya_lo : nullptr;
+  unsigned char* nxt_lo = use_lo ? w + B.dyb_lo : nullptr;
+  if ((rc = run_dgrad16(w + B.ds, use_lo ? w + B.ds_lo : nullptr, 128, fold + kFoldW, 256, 0, M(7), g_raw + 3, 4, params[kSigmaW], cur,
+                        cur_lo, state, ST_AMAX_DS, ST_SCALE_DS, ST_L1_FOLD, ST_AMAX_H0 + 7, ST_SCALE_H0 + 7, P, st)))
     return rc;
   for (int l = 7; l >= 1; --l) {
     const int ldw = l == 4 ? 319 : 256;
@@ -256,10 +273,11 @@ int field_backward16(const float* const* params, float* const* grads, int new_ac
     } else {
       if ((rc = run_wgrad16(cur, 256, H(l - 1), 256, 256, grads[2 * l], ldw, 0, grads[2 * l + 1], sc, nullptr, nullptr, nullptr, ppad, st))) return rc;
     }
-    if ((rc = run_dgrad16(cur, 256, params[2 * l], ldw, l == 4 ? kXyzCh : 0, M(l - 1), nullptr, 0, nullptr, nxt, state,
-                          ST_AMAX_H0 + l, ST_SCALE_H0 + l, ST_L1_L0 + l, ST_AMAX_H0 + l - 1, ST_SCALE_H0 + l - 1, P, st)))
+    if ((rc = run_dgrad16(cur, cur_lo, 256, params[2 * l], ldw, l == 4 ? kXyzCh : 0, M(l - 1), nullptr, 0, nullptr, nxt, nxt_lo,
+                          state, ST_AMAX_H0 + l, ST_SCALE_H0 + l, ST_L1_L0 + l, ST_AMAX_H0 + l - 1, ST_SCALE_H0 + l - 1, P, st)))
       return rc;
     unsigned char* t = cur; cur = nxt; nxt = t;
+    t = cur_lo; cur_lo = nxt_lo; nxt_lo = t;
   }
   // layer 1: weights only
   return run_wgrad16(cur, 256, act + A.enc, kXyzPad, kXyzCh, grads[0], 63, 0, grads[1], state + ST_SCALE_H0, nullptr, nullptr, nullptr, ppad, st);

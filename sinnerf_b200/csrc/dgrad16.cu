@@ -8,7 +8,11 @@
 // already 16-bit in HBM:
 //   * dY (Ppad, N) fp16 in the T32 layout, stored as true * s_in: lane = point, an 8-feature cell is 16 bytes,
 //     32 lanes = 512 contiguous bytes: the loaders do LDG.128 -> tcgen05.st, no conversion, no transposition;
-//   * W^T as fp16 hi + lo, 2 products per K step (was 3 with bf16 hi/lo on both operands);
+//   * the gradient CHAIN (dgrad -> dgrad) is carried as fp16 hi + lo planes (22 bits), so rounding does not
+//     accumulate over the 8 layers; the wgrad of each layer reads only the hi plane -- its error is ONE fp16
+//     rounding of that layer's gradient, whatever the depth (measured: hi-only chains reached 1.1e-3 on the first
+//     layer's weights, hi + lo 2e-4; the parity bar is 1e-3).  kLo = false is the hi-only variant (SNB_BWD16_LO=0);
+//   * W^T as fp16 hi + lo; products hi*hi + lo*hi + hi*lo (2 without the lo plane);
 //   * the epilogue multiplies by the power-of-two ratio s_out / s_in, adds the sigma head's rank-1 term,
 //     applies the ReLU mask (bit words the forward wrote, 32 B per point), rounds to fp16 and writes cells of
 //     the output T32 tensor -- 4 x 512 contiguous bytes per warp and 32 columns; it also raises the running
@@ -16,7 +20,8 @@
 //   * s_out = the largest power of two with  (max |dY| / s_in) * (max column L1 norm of W) [+ max |extra| max |evec|]
 //     * s_out <= 2^14: a rigorous bound, so the fp16 stores cannot overflow; chosen identically by every CTA
 //     from three device scalars (no host round trip).
-// HBM per point and layer: 2 N + 32 B in, 512 B out (was 4 N + 32 in, 1 KB out).
+// HBM per point and layer: 4 N + 32 B in, 1 KB out with the lo plane (the fp32 version moved the same bytes but
+// spent its warps converting them, and its wgrad read 2 KB where wgrad16 reads 1 KB); 2 N + 32 in, 512 B out without.
 #include <cuda_fp16.h>
 
 #include "act16.cuh"
@@ -33,15 +38,17 @@ constexpr int kDgTile = 128;                 // points per CTA (MMA M = 256 acro
 constexpr int kDgConvWarps = 8, kDgEpiWarps = 4;      // loaders: two warps per TMEM lane quadrant
 constexpr int kDgMmaWarp = kDgConvWarps + kDgEpiWarps;
 constexpr int kDgThreads = (kDgMmaWarp + 1) * 32;
-constexpr uint32_t kDgColD = 0, kDgColA = 256;
+constexpr uint32_t kDgColD = 0, kDgColA = 256, kDgColAlo = 384;
 
 struct Dgrad16Args {
   const unsigned char* dY;         // (Ppad, NRED) fp16 T32, stored as true * state[st_scale_in]
+  const unsigned char* dY_lo;      // same shape: fp16(true * s - hi) (kLo)
   const float* W; int ldw; int col_off;   // nn.Linear weight (NRED, ldw); inputs [col_off, col_off + 256)
   const uint32_t* mask;            // (8 words, Ppad) nullable: bit c of word w = [input[p][32 w + c] > 0]
   const float* extra; int extra_stride;   // nullable per-point scalar (true units)
   const float* evec;               // (256), with extra
   unsigned char* dX;               // (Ppad, 256) fp16 T32, stored as true * state[st_scale_out]
+  unsigned char* dX_lo;            // residual plane (kLo)
   float* state;                    // Bwd16 state words (act16.cuh)
   int st_amax_in, st_scale_in, st_l1, st_amax_out, st_scale_out;
   long long P, ppad;
@@ -65,7 +72,7 @@ __device__ __forceinline__ void f16_split_pair(float x0, float x1, uint32_t& hi,
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int NRED>
+template <int NRED, bool kLo>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad16_kernel(Dgrad16Args a) {
   using S = Dg16Smem<NRED>;
   constexpr int kQ = NRED / 64;               // K quarters (64 reduction columns each)
@@ -141,6 +148,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
             for (int ks = q * 4; ks < q * 4 + 4; ++ks) {
               const uint32_t a_t = tbase + kDgColA + ks * 8;
               mma2_ts_lohi(d, a_t, bh + ks * kStepB, b_hi32, idesc, ks > 0 ? 1u : 0u);
+              if (kLo) mma2_ts_lohi(d, tbase + kDgColAlo + ks * 8, bh + ks * kStepB, b_hi32, idesc, 1u);
               mma2_ts_lohi(d, a_t, bl + ks * kStepB, b_hi32, idesc, 1u);
             }
             if (h == 1) mma2_commit(&s.q_free[q]);      // both halves have consumed A quarter q
@@ -158,29 +166,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
     const int quad = warp & 3, sub = warp >> 2;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const long long n_units = n_slots * kQ;
-    auto load_unit = [&](long long u, uint4 (&v)[4]) {
+    struct Unit { uint4 h[4]; uint4 l[kLo ? 4 : 1]; };
+    auto load_unit = [&](long long u, Unit& v) {
       const long long slot = u / kQ;
       const int q = (int)(u - slot * kQ);
       const long long pt = tile_of(slot) * kDgTile + quad * 32 + lane;
+      const bool ok = u < n_units && pt < a.ppad;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        v[c] = (u < n_units && pt < a.ppad) ? __ldg(reinterpret_cast<const uint4*>(a.dY + a16_cell(pt, q * 8 + sub * 4 + c, NRED)))
-                                            : make_uint4(0u, 0u, 0u, 0u);
+      for (int c = 0; c < 4; ++c) {
+        const size_t off = a16_cell(pt, q * 8 + sub * 4 + c, NRED);
+        v.h[c] = ok ? __ldg(reinterpret_cast<const uint4*>(a.dY + off)) : make_uint4(0u, 0u, 0u, 0u);
+        if (kLo) v.l[c] = ok ? __ldg(reinterpret_cast<const uint4*>(a.dY_lo + off)) : make_uint4(0u, 0u, 0u, 0u);
+      }
     };
-    auto store_unit = [&](long long u, const uint4 (&v)[4]) {
+    auto store_unit = [&](long long u, const Unit& v) {
       const long long slot = u / kQ;
       const int q = (int)(u - slot * kQ);
       uint32_t w[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { w[4 * c] = v[c].x; w[4 * c + 1] = v[c].y; w[4 * c + 2] = v[c].z; w[4 * c + 3] = v[c].w; }
+      for (int c = 0; c < 4; ++c) { w[4 * c] = v.h[c].x; w[4 * c + 1] = v.h[c].y; w[4 * c + 2] = v.h[c].z; w[4 * c + 3] = v.h[c].w; }
       if (slot > 0) { mbar_wait(&s.q_free[q], (uint32_t)(slot - 1) & 1); tc_fence_after(); }
       tmem_st16(tbase + lane_base + kDgColA + q * 32 + sub * 16, w);
+      if (kLo) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { w[4 * c] = v.l[c].x; w[4 * c + 1] = v.l[c].y; w[4 * c + 2] = v.l[c].z; w[4 * c + 3] = v.l[c].w; }
+        tmem_st16(tbase + lane_base + kDgColAlo + q * 32 + sub * 16, w);
+      }
       tmem_wait_st();
       tc_fence_before();
       signal(&s.q_ready[q]);
     };
     {
-      uint4 x[4], y[4], z[4];
+      Unit x, y, z;
       load_unit(0, x);
       load_unit(1, y);
       for (long long u = 0; u < n_units; u += 3) {      // three units in flight per thread
@@ -217,7 +234,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
           tmem_ld32(tbase + lane_base + kDgColD + c0, v);
           tmem_wait_ld();
           if (g == 3) { tc_fence_before(); signal(&s.d_drained[h]); }   // half h is in registers
-          uint32_t o[16];
+          uint32_t o[16], ol[kLo ? 16 : 1];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float2 e = *reinterpret_cast<const float2*>(s.evec + c0 + 2 * j);
@@ -227,11 +244,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
             x1 = (mw[g] >> (2 * j + 1)) & 1u ? x1 : 0.f;
             amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
             o[j] = pack_half2_sat(x0, x1);
+            if (kLo) {
+              const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(&o[j]));
+              ol[j] = pack_half2_sat(x0 - hv.x, x1 - hv.y);
+            }
           }
           if (inbuf) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
               *reinterpret_cast<uint4*>(a.dX + a16_cell(pt, (c0 >> 3) + c, 256)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+            if (kLo) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(a.dX_lo + a16_cell(pt, (c0 >> 3) + c, 256)) = make_uint4(ol[4 * c], ol[4 * c + 1], ol[4 * c + 2], ol[4 * c + 3]);
+            }
           }
         }
       }
@@ -247,31 +273,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
   if (warp == kDgMmaWarp) tmem_dealloc_pair(tbase);
 }
 
-template <int NRED>
+template <int NRED, bool kLo>
 int launch_dgrad16(const Dgrad16Args& a, cudaStream_t st) {
   static SmemOptIn optin;
   const int smem = (int)sizeof(Dg16Smem<NRED>) + 1024;
-  if (int rc = ensure_smem(dgrad16_kernel<NRED>, optin, smem, "dgrad16")) return rc;
+  if (int rc = ensure_smem(dgrad16_kernel<NRED, kLo>, optin, smem, "dgrad16")) return rc;
   const int sms = sm_count();
   const long long ntiles = (a.P + kDgTile - 1) / kDgTile;
   long long pairs = (ntiles + 1) / 2;
   if (pairs > sms / 2) pairs = sms / 2;
-  dgrad16_kernel<NRED><<<(unsigned)(2 * pairs), kDgThreads, smem, st>>>(a);
+  dgrad16_kernel<NRED, kLo><<<(unsigned)(2 * pairs), kDgThreads, smem, st>>>(a);
   return check_launch("dgrad16_kernel");
 }
 
 }  // namespace
 
-// dY (Ppad, N) -> dX (Ppad, 256), both fp16 T32; scales and running maxima live in `state` (act16.cuh)
-int run_dgrad16(const void* dY, int N, const float* W, int ldw, int col_off, const uint32_t* mask, const float* extra,
-                int extra_stride, const float* evec, void* dX, float* state, int st_amax_in, int st_scale_in, int st_l1,
-                int st_amax_out, int st_scale_out, long long P, cudaStream_t st) {
+// dY (Ppad, N) -> dX (Ppad, 256), fp16 T32 hi (+ lo) planes; scales and running maxima live in `state` (act16.cuh).
+// dY_lo / dX_lo both NULL = the hi-only variant.
+int run_dgrad16(const void* dY, const void* dY_lo, int N, const float* W, int ldw, int col_off, const uint32_t* mask,
+                const float* extra, int extra_stride, const float* evec, void* dX, void* dX_lo, float* state, int st_amax_in,
+                int st_scale_in, int st_l1, int st_amax_out, int st_scale_out, long long P, cudaStream_t st) {
   if (P == 0) return SNB_OK;
-  Dgrad16Args a{reinterpret_cast<const unsigned char*>(dY), W, ldw, col_off, mask, extra, extra_stride, evec,
-                reinterpret_cast<unsigned char*>(dX), state, st_amax_in, st_scale_in, st_l1, st_amax_out, st_scale_out,
-                P, a16_pad(P)};
-  if (N == 256) return launch_dgrad16<256>(a, st);
-  if (N == 128) return launch_dgrad16<128>(a, st);
+  if ((dY_lo == nullptr) != (dX_lo == nullptr)) return fail(SNB_ERR_INVALID, "run_dgrad16: lo planes must be given for both tensors or none");
+  Dgrad16Args a{reinterpret_cast<const unsigned char*>(dY), reinterpret_cast<const unsigned char*>(dY_lo), W, ldw, col_off, mask,
+                extra, extra_stride, evec, reinterpret_cast<unsigned char*>(dX), reinterpret_cast<unsigned char*>(dX_lo), state,
+                st_amax_in, st_scale_in, st_l1, st_amax_out, st_scale_out, P, a16_pad(P)};
+  const bool lo = dY_lo != nullptr;
+  if (N == 256) return lo ? launch_dgrad16<256, true>(a, st) : launch_dgrad16<256, false>(a, st);
+  if (N == 128) return lo ? launch_dgrad16<128, true>(a, st) : launch_dgrad16<128, false>(a, st);
   return fail(SNB_ERR_INVALID, "run_dgrad16: unsupported reduction length %d", N);
 }
 

@@ -1,7 +1,8 @@
 // wgrad16.cu -- weight gradients of one nn.Linear from 16-bit T32 operands (act16.cuh), on tensor cores.
 //
 //   dW[n][col_off + k] += (1 / scale) * sum_p dY[p][n] X[p][k]        db[n] += (1 / scale) * sum_p dY[p][n]
-//   optional head rows:  dH[r][k] += (1 / scale2) * sum_p hg[p][r] X[p][k],  r < 8   (sigma / rgb head weights)
+//   optional head rows:  dH[r][k] += (1 / scale2) * sum_p (hg[p][r] + hg[p][r + 4]) X[p][k],  r < 4   (sigma / rgb head
+//                        weights; features r + 4 of the hg cell hold the fp16 rounding residual of feature r)
 //
 // (reference: autograd of `nn.Linear` inside models/nerf.py:105-148.)  dY, X and hg are fp16 tensors in
 // the T32 layout: a 32-point tile copied verbatim into shared memory IS the MN-major SWIZZLE_NONE canonical
@@ -217,9 +218,10 @@ __global__ void __launch_bounds__(kW16Threads, 1) wgrad16_kernel(W16Args a) {
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kW16EpiWarps * 32) : "memory");
         if (head) {
-          for (int e = tid; e < 8 * FB; e += kW16EpiWarps * 32) {
+          // features 4..7 of the hg cell are the fp16 residuals of features 0..3: row r + row r + 4
+          for (int e = tid; e < 4 * FB; e += kW16EpiWarps * 32) {
             const int r = e / FB, k = e - r * FB;
-            if (a.dH[r] != nullptr && k < a.K) atomicAdd(a.dH[r] + k, out[r * kLd + k]);
+            if (a.dH[r] != nullptr && k < a.K) atomicAdd(a.dH[r] + k, out[r * kLd + k] + out[(r + 4) * kLd + k]);
           }
         } else if (a.K == FB && ((a.ldw | a.col_off) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dW) & 15) == 0) {
           for (int e = tid; e < 128 * (FB / 4); e += kW16EpiWarps * 32) {
