@@ -542,7 +542,11 @@ __global__ void __launch_bounds__(128) importance_merge_kernel(
         continue;
       }
     }
-    {
+    // deterministic u (inference): the new depths come out ascending -- nothing to sort (this check replaces the
+    // O(Ni^2) rank sort that made the kernel 354 us per 160k-ray frame in round 1)
+    bool new_sorted = true;
+    for (int j = lane; j + 1 < Ni; j += 32) new_sorted &= zn[j] <= zn[j + 1];
+    if (!__all_sync(kFull, new_sorted)) {
       float mine[8];                       // Ni <= 256
       int rk[8];
       int cnt = 0;
