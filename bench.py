@@ -342,7 +342,7 @@ def bench_configs_4_train(dev, rank, local_rank, world, precision, flush, sync_a
             super().__init__()
             self.nerf_coarse, self.nerf_fine = ms
 
-        def forward(self):
+        def forward(self, _step):        # DDP's pre-forward needs at least one positional input
             res = rendering.render_rays_multi([self.nerf_coarse, self.nerf_fine], emb, batches, N_SAMPLES, False, 1.0, 1.0,
                                               N_IMPORTANCE, 32768, True, precision=precision, batch_losses=specs)
             loss = res[0]["loss_rgb"] + 0.1 * res[0]["loss_depth"]
@@ -356,7 +356,7 @@ def bench_configs_4_train(dev, rank, local_rank, world, precision, flush, sync_a
 
     def step():
         opt.zero_grad(set_to_none=True)
-        net().backward()
+        net(0).backward()
         opt.step()
     for _ in range(3):
         step()
