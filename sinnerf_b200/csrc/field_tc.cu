@@ -869,12 +869,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
               float x[4];
               if (kRelu && !kSigma && kTrain == 0) {
                 // nobody needs the fp32 post-activation value: ReLU and the fp16 range guard ride on the converts
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const float2 bb = b2[j + e];
-                  split_pair_relu<kBf16, kSplit>(__uint_as_float(v[2 * (j + e)]) + bb.x, __uint_as_float(v[2 * (j + e) + 1]) + bb.y,
-                                                 v[2 * (j + e)], v[2 * (j + e) + 1]);
-                }
+                // one 16-byte bias load and two packed fp32x2 adds (FADD2) per four columns
+                const float4 bb = *reinterpret_cast<const float4*>(b2 + j);
+                const float2 x01 = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), make_float2(bb.x, bb.y));
+                const float2 x23 = __fadd2_rn(make_float2(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), make_float2(bb.z, bb.w));
+                split_pair_relu<kBf16, kSplit>(x01.x, x01.y, v[2 * j], v[2 * j + 1]);
+                split_pair_relu<kBf16, kSplit>(x23.x, x23.y, v[2 * j + 2], v[2 * j + 3]);
                 continue;
               }
 #pragma unroll
@@ -1030,377 +1030,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   if (warp == kMmaWarp) { if (kCg == 2) tmem_dealloc_pair(tbase); else tmem_dealloc<512>(tbase); }
 }
 
-// ------------------------------------------------------------------ bf16 "ping-pong" kernel
-// SNB_PREC_BF16 (single product) is not tensor-bound in field_tc_kernel: an MMA phase of a layer half is 512
-// cycles, the epilogue that turns its accumulator into the next layer's operand has ~1000-1400 cycles of latency,
-// and the 528 KB of weights a CTA streams per 128-point tile take 18.9k cycles of L2 ingest against 16.5k cycles
-// of MMA (round 1: tensor pipe 46.9 %).  Here a CTA owns TWO 128-point tiles per slot:
-//   * every weight chunk is staged once and multiplied against both tiles (ingest per point halved);
-//   * the epilogue of one tile runs under the MMAs of the other one (warps 0-7 serve tile 0, warps 8-15 tile 1;
-//     a warp owns 64 columns of its TMEM lane quadrant);
-//   * TMEM: one 128-column accumulator per tile (a layer's two output halves go through it one after the
-//     other) + the tile's A operand (256 K x bf16 = 128 columns): 2 x (128 + 128) = 512 columns.
-// Per chunk the issuer multiplies tile 0, then tile 1; per (layer, half, tile) the hand-offs are
-//   d_full[t]    MMA -> epilogue   the accumulator of tile t is complete
-//   d_drained[t] epilogue -> MMA   ... has been read into registers (the next accumulate = 0 may overwrite it)
-//   a_ready[t][q] epilogue -> MMA  K half q of tile t's next operand is stored
-//   a_free[t]    MMA -> epilogue   this layer's last reader of A_t[k < 128] has retired (half a's results may go in)
-// Same packed image, same chunk order, same products and roundings of the hidden activations as
-// field_tc_kernel<bf16>; the sigma / rgb head dot products are summed in a different order (64-column groups), so
-// results agree with the single-tile kernel to fp32 rounding of the heads (tests/test_gpu_round2.py, A/B by env).
-constexpr uint32_t kPpColD = 0, kPpColA = 256;
-
-struct PpSmem {
-  static constexpr uint32_t kStageBytes = Geo<2>::kPartBytesMax;              // 16 KB: this CTA's share of a K = 128 chunk
-  static constexpr int kStages = 9;
-  alignas(1024) unsigned char ring[kStages][kStageBytes];
-  alignas(128) unsigned char enc[2][kTile * kXyzPad * 2];    // per tile, canonical [k8][row][8] bf16
-  alignas(128) unsigned char dir[2][kTile * kDirPad * 2];
-  alignas(16) float cst[kConstFloats];
-  float sigp[2][2][kTile];          // [tile][column group] sigma partial sums
-  float rgbp[2][2][3][kTile];
-  uint64_t full[kStages], empty[kStages];
-  uint64_t d_full[2], d_drained[2], a_ready[2][2], a_free[2], enc_ready[2], dir_ready[2];
-  uint32_t tmem_base;
-};
-
-template <bool kUnused = false>
-__global__ void __launch_bounds__(kThreads, 1) field_pp_kernel(TcParams p) {
-  using G = Geo<2>;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  PpSmem& s = *reinterpret_cast<PpSmem*>(smem_raw);
-  constexpr ConstLayout CL = make_const_layout();
-  constexpr uint32_t kStageBytes = PpSmem::kStageBytes;
-  constexpr int kStages = PpSmem::kStages;
-  const ChunkTable& tab = chunk_table<2>();
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(p.image);
-  const int new_activation = hdr->new_activation;
-  const float* g_cst = reinterpret_cast<const float*>(p.image + sizeof(PackedHeader));
-  const unsigned char* g_chunks = p.image + sizeof(PackedHeader) + kConstBytes;
-  const uint32_t cta_rank = cluster_ctarank();
-  const bool leader = cta_rank == 0;
-  // a slot of a CTA pair = 4 tiles (2 per CTA); slots past the end compute on zeros and store nothing
-  const long long ntiles = (p.n_points + kTile - 1) / kTile;
-  const long long n_groups = gridDim.x / 2, group = blockIdx.x / 2;
-  const long long n_slots = ((ntiles + 3) / 4 + n_groups - 1) / n_groups;
-  const int n_chunks = p.sigma_only ? tab.n_sigma_only : tab.n_total;
-
-  for (int i = tid; i < kConstFloats; i += kThreads) s.cst[i] = g_cst[i];
-  if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], leader ? 2 : 1); mbar_init(&s.empty[i], 1); }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s.d_full[t], 1);
-      mbar_init(&s.a_free[t], 1);
-      mbar_init(&s.d_drained[t], 8 * 32 * 2);       // the 8 warps of tile t's group in both CTAs
-      mbar_init(&s.a_ready[t][0], 8 * 32 * 2);
-      mbar_init(&s.a_ready[t][1], 8 * 32 * 2);
-      mbar_init(&s.enc_ready[t], 8 * 32 * 2);
-      mbar_init(&s.dir_ready[t], 8 * 32 * 2);
-    }
-    fence_mbar_init();
-  }
-  if (warp == kMmaWarp) tmem_alloc_pair(&s.tmem_base);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tbase = s.tmem_base;
-
-  if (warp == kLoadWarp) {
-    // ======================= weight loader: every chunk once per slot (= per 2 tiles of this CTA) =======================
-    if (elect_one()) {
-      uint32_t it = 0;
-      for (long long slot = 0; slot < n_slots; ++slot) {
-        for (int ci = 0; ci < n_chunks; ++ci, ++it) {
-          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(&s.empty[st], ph ^ 1);
-          const Chunk c = tab.c[ci];
-          const uint32_t share = G::kStepBytes * c.steps;
-          const unsigned char* src = g_chunks + (size_t)c.off * (G::kStepBytes * 2) + (size_t)cta_rank * share;
-          mbar_arrive_expect_tx(&s.full[st], share);
-          bulk_g2s(s.ring[st], src, share, &s.full[st]);
-        }
-      }
-    }
-  } else if (warp == kMmaWarp && !leader) {
-    // ======================= relay (odd CTA): "my share of the chunk has landed" =======================
-    if (elect_one()) {
-      uint32_t it = 0;
-      for (long long slot = 0; slot < n_slots; ++slot) {
-        for (int ci = 0; ci < n_chunks; ++ci, ++it) {
-          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(&s.full[st], ph);
-          mbar_arrive_remote(&s.full[st], 0);
-        }
-      }
-    }
-  } else if (warp == kMmaWarp) {
-    // ======================= MMA issuer (leader CTA, one elected lane, schedule unrolled at compile time) =======
-    if (elect_one()) {
-      constexpr ChunkTable T = make_chunk_table<G::kKc>();
-      const uint32_t idesc = make_idesc(kFmtBF16, kTile * 2, kNh);
-      const uint64_t desc_b0 = make_smem_desc(0, G::kRowsB * 16, 128);
-      const uint64_t desc_a0 = make_smem_desc(0, kTile * 16, 128);
-      const uint32_t bd_hi32 = (uint32_t)(desc_b0 >> 32), ad_hi32 = (uint32_t)(desc_a0 >> 32);
-      const uint32_t b_ring0 = (uint32_t)desc_b0 + (smem_u32(s.ring[0]) >> 4);
-      const uint32_t a_enc[2] = {(uint32_t)desc_a0 + (smem_u32(s.enc[0]) >> 4), (uint32_t)desc_a0 + (smem_u32(s.enc[1]) >> 4)};
-      const uint32_t a_dir[2] = {(uint32_t)desc_a0 + (smem_u32(s.dir[0]) >> 4), (uint32_t)desc_a0 + (smem_u32(s.dir[1]) >> 4)};
-      constexpr uint32_t kStepB = (2 * G::kRowsB * 16) >> 4;
-      constexpr uint32_t kStepA = (2 * kTile * 16) >> 4;
-      uint32_t st = 0, ph_full = 0;
-      uint32_t dd_par[2] = {0, 0}, ar_par[2][2] = {{0, 0}, {0, 0}};
-      for (long long slot = 0; slot < n_slots; ++slot) {
-        const uint32_t slot_par = (uint32_t)slot & 1;
-        static_for<T.n_total>([&](auto tag) {
-          constexpr int CI = decltype(tag)::value;
-          constexpr Chunk c = T.c[CI];
-          if (CI >= T.n_sigma_only && p.sigma_only) return;
-          mbar_wait(&s.full[st], ph_full);
-          const uint32_t bh = b_ring0 + st * (kStageBytes >> 4);
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (c.first && !(c.layer == 0 && c.half == 0 && slot == 0)) { mbar_wait(&s.d_drained[t], dd_par[t]); dd_par[t] ^= 1; }
-            if (c.src == SRC_ENC && c.layer == 0) mbar_wait(&s.enc_ready[t], slot_par);
-            if (c.src == SRC_DIR) mbar_wait(&s.dir_ready[t], slot_par);
-            if (c.src == SRC_HID && c.half == 0) {
-              constexpr int q = c.a16 >= 8 ? 1 : 0;
-              mbar_wait(&s.a_ready[t][q], ar_par[t][q]); ar_par[t][q] ^= 1;
-            }
-            tc_fence_after();
-            const uint32_t d = tbase + kPpColD + t * 128;
-            if (c.src == SRC_HID) {
-              const uint32_t a_t = tbase + kPpColA + t * 128 + (uint32_t)c.a16 * 8;
-#pragma unroll
-              for (int ks = 0; ks < c.steps; ++ks)
-                mma2_ts_lohi(d, a_t + ks * 8, bh + ks * kStepB, bd_hi32, idesc, (ks == 0 && c.first) ? 0u : 1u);
-            } else {
-              constexpr uint32_t a_off = ((uint32_t)c.a16 * 2 * (kTile * 16)) >> 4;
-              const uint32_t ah = (c.src == SRC_ENC ? a_enc[t] : a_dir[t]) + a_off;
-#pragma unroll
-              for (int ks = 0; ks < c.steps; ++ks)
-                mma2_ss_lohi(d, ah + ks * kStepA, ad_hi32, bh + ks * kStepB, bd_hi32, idesc, (ks == 0 && c.first) ? 0u : 1u);
-            }
-            if (c.commit & COMMIT_AFREE) mma2_commit(&s.a_free[t]);
-            if (c.commit & (COMMIT_D0 | COMMIT_D1)) mma2_commit(&s.d_full[t]);
-          }
-          mma2_commit(&s.empty[st]);
-          if (++st == kStages) { st = 0; ph_full ^= 1; }
-        });
-      }
-    }
-    __syncwarp();
-  } else {
-    // ======================= prologue / epilogue warps: group t = warp / 8 serves tile t =======================
-    const int t = warp >> 3;
-    const int quad = warp & 3, cg = (warp >> 2) & 1;          // TMEM lane quadrant, 64-column group of a 128-column half
-    const int row = quad * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    auto signal = [&](uint64_t* bar) { if (!leader) mbar_arrive_remote(bar, 0); else mbar_arrive(bar); };
-    auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory"); };
-    auto tile_of = [&](long long slot) { return ((group + slot * n_groups) * 2 + cta_rank) * 2 + t; };
-    uint32_t ph_d = 0, ph_free = 0;
-    auto put8 = [&](unsigned char* base, int k8, const float (&v)[8]) {
-      uint32_t h[4], l_unused;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) split_pair<true, false>(v[2 * j], v[2 * j + 1], h[j], l_unused);
-      *reinterpret_cast<uint4*>(base + (uint32_t)k8 * (kTile * 16) + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-    };
-    auto embed8 = [&](const float (&x)[3], int c_lo, int n_ch, int n_freqs, float (&v)[8]) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (c_lo + j < 3) ? x[(c_lo + j) % 3] : 0.f;
-      for (int f = 0; f < n_freqs; ++f) {
-        const int base = 3 + 6 * f;
-        if (base + 6 <= c_lo || base >= c_lo + 8) continue;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int js = base + c - c_lo, jc = js + 3;
-          if ((js >= 0 && js < 8) || (jc >= 0 && jc < 8)) {
-            float sn, cs;
-            sincosf(x[c] * (float)(1 << f), &sn, &cs);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (j == js) v[j] = sn;
-              if (j == jc && base + 3 + c < n_ch) v[j] = cs;
-            }
-          }
-        }
-      }
-    };
-    // xyz embedding of this group's tile: a thread writes 32 of its row's 64 channels, 16 per part
-    auto encode_xyz = [&](long long slot, int part) {
-      const long long pt = tile_of(slot) * kTile + row;
-      float x[3] = {0.f, 0.f, 0.f};
-      if (pt < p.n_points) {
-        const long long ray = pt / p.n_samples;
-        const float4 r0 = *reinterpret_cast<const float4*>(p.rays + ray * 8);
-        const float4 r1 = *reinterpret_cast<const float4*>(p.rays + ray * 8 + 4);
-        const float zz = p.z[pt];
-        x[0] = __fadd_rn(r0.x, __fmul_rn(r0.w, zz));   // rendering.py:284-285 rounding
-        x[1] = __fadd_rn(r0.y, __fmul_rn(r1.x, zz));
-        x[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, zz));
-      }
-#pragma unroll 1
-      for (int g = 0; g < 2; ++g) {
-        const int c_lo = (cg * 4 + part * 2 + g) * 8;
-        float v[8];
-        embed8(x, c_lo, kXyzCh, SNB_XYZ_FREQS, v);
-        put8(s.enc[t], c_lo / 8, v);
-      }
-      if (part == 1) { fence_proxy_async_smem(); signal(&s.enc_ready[t]); }
-    };
-    auto encode_dir = [&](long long slot) {
-      const long long pt = tile_of(slot) * kTile + row;
-      float d[3] = {0.f, 0.f, 0.f};
-      if (pt < p.n_points) {
-        const long long ray = pt / p.n_samples;
-        d[0] = p.rays[ray * 8 + 3]; d[1] = p.rays[ray * 8 + 4]; d[2] = p.rays[ray * 8 + 5];
-      }
-#pragma unroll 1
-      for (int g = 0; g < 2; ++g) {
-        const int c_lo = (cg * 2 + g) * 8;
-        float v[8];
-        embed8(d, c_lo, kDirCh, SNB_DIR_FREQS, v);
-        put8(s.dir[t], c_lo / 8, v);
-      }
-      fence_proxy_async_smem();
-      signal(&s.dir_ready[t]);
-    };
-
-    if (n_slots > 0) { encode_xyz(0, 0); encode_xyz(0, 1); }
-    for (long long slot = 0; slot < n_slots; ++slot) {
-      const long long pt = tile_of(slot) * kTile + row;
-      float sig_part = 0.f;
-      for (int l = 0; l < 8; ++l) {
-        const float* bias = s.cst + CL.b[l];
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&s.d_full[t], ph_d); ph_d ^= 1;
-          tc_fence_after();
-          const int c0 = h * kNh + cg * 64;                 // output columns == next layer's k
-          uint32_t packed[32];
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            uint32_t v[32];
-            tmem_ld32(tbase + lane_base + kPpColD + t * 128 + cg * 64 + b * 32, v);
-            tmem_wait_ld();
-            if (b == 1) { tc_fence_before(); signal(&s.d_drained[t]); }     // the accumulator is in registers
-            const float2* b2 = reinterpret_cast<const float2*>(bias + c0 + b * 32);
-            const float2* w2 = reinterpret_cast<const float2*>(s.cst + CL.sigma_w + c0 + b * 32);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 bb = b2[j];
-              const float x0 = __uint_as_float(v[2 * j]) + bb.x, x1 = __uint_as_float(v[2 * j + 1]) + bb.y;
-              if (l == 7) {
-                const float2 ww = w2[j];
-                sig_part = fmaf(fmaxf(x0, 0.f), ww.x, sig_part); sig_part = fmaf(fmaxf(x1, 0.f), ww.y, sig_part);
-              }
-              uint32_t lo_unused;
-              split_pair_relu<true, false>(x0, x1, packed[b * 16 + j], lo_unused);
-            }
-          }
-          if (h == 0) { mbar_wait(&s.a_free[t], ph_free); ph_free ^= 1; tc_fence_after(); }
-          if (!(l == 7 && p.sigma_only)) {
-            tmem_st32(tbase + lane_base + kPpColA + t * 128 + (c0 >> 1), packed);
-            tmem_wait_st();
-            tc_fence_before();
-            signal(&s.a_ready[t][h]);
-          }
-        }
-        if (l == 0 && !p.sigma_only) encode_dir(slot);
-        if (l == 5 && slot + 1 < n_slots) encode_xyz(slot + 1, 0);
-        if (l == 6 && slot + 1 < n_slots) encode_xyz(slot + 1, 1);
-        if (l == 7) {
-          s.sigp[t][cg][row] = sig_part;
-          group_sync();
-          if (cg == 0) {
-            const float sg = (s.sigp[t][0][row] + s.sigp[t][1][row]) + s.cst[CL.sigma_b];
-            s.sigp[t][0][row] = sg;
-            if (p.sigma_only && pt < p.n_points) p.out[pt] = sg;
-          }
-          group_sync();
-        }
-      }
-      if (p.sigma_only) continue;
-      // ---------------- direction layer epilogue + rgb head + output
-      {
-        mbar_wait(&s.d_full[t], ph_d); ph_d ^= 1;
-        tc_fence_after();
-        const float* bias = s.cst + CL.b[9];
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        const float sh = new_activation ? 1.0f : 0.0f;
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          uint32_t v[32];
-          const int c0 = cg * 64 + b * 32;
-          tmem_ld32(tbase + lane_base + kPpColD + t * 128 + c0, v);
-          tmem_wait_ld();
-          if (b == 1) { tc_fence_before(); signal(&s.d_drained[t]); }
-          const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
-          const float4* w0 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + c0);
-          const float4* w1 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + kHalf + c0);
-          const float4* w2 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + 2 * kHalf + c0);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = b4[j4], r0 = w0[j4], r1 = w1[j4], r2 = w2[j4];
-            float x[4] = {__uint_as_float(v[4 * j4]) + (bb.x - sh), __uint_as_float(v[4 * j4 + 1]) + (bb.y - sh),
-                          __uint_as_float(v[4 * j4 + 2]) + (bb.z - sh), __uint_as_float(v[4 * j4 + 3]) + (bb.w - sh)};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = new_activation ? softplus_fast(x[e]) : fmaxf(x[e], 0.f);
-            a0 = fmaf(x[0], r0.x, a0); a0 = fmaf(x[1], r0.y, a0); a0 = fmaf(x[2], r0.z, a0); a0 = fmaf(x[3], r0.w, a0);
-            a1 = fmaf(x[0], r1.x, a1); a1 = fmaf(x[1], r1.y, a1); a1 = fmaf(x[2], r1.z, a1); a1 = fmaf(x[3], r1.w, a1);
-            a2 = fmaf(x[0], r2.x, a2); a2 = fmaf(x[1], r2.y, a2); a2 = fmaf(x[2], r2.z, a2); a2 = fmaf(x[3], r2.w, a2);
-          }
-        }
-        s.rgbp[t][cg][0][row] = a0; s.rgbp[t][cg][1][row] = a1; s.rgbp[t][cg][2][row] = a2;
-        group_sync();
-        if (cg == 0 && pt < p.n_points) {
-          float c[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float x = (s.rgbp[t][0][k][row] + s.rgbp[t][1][k][row]) + s.cst[CL.rgb_b + k];
-            c[k] = new_activation ? widened_sigmoid_f(x) : sigmoid_f(x);
-          }
-          reinterpret_cast<float4*>(p.out)[pt] = make_float4(c[0], c[1], c[2], s.sigp[t][0][row]);
-        }
-        group_sync();
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == kMmaWarp) tmem_dealloc_pair(tbase);
-}
-
-static int launch_pp(const TcParams& p, cudaStream_t st) {
-  static SmemOptIn optin;
-  const long long ntiles = (p.n_points + kTile - 1) / kTile;
-  if (ntiles == 0) return SNB_OK;
-  const size_t smem = sizeof(PpSmem) + 1024;
-  auto kern = field_pp_kernel<false>;
-  if (int rc = ensure_smem(kern, optin, (int)smem, "field_pp")) return rc;
-  const int sms = sm_count();
-  long long groups = (ntiles + 3) / 4;
-  if (groups > sms / 2) groups = sms / 2;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(groups * 2));
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  TcParams pd = p;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, pd);
-  if (e != cudaSuccess) return fail(SNB_ERR_CUDA, "field_pp_kernel launch: %s", cudaGetErrorString(e));
-  return check_launch("field_pp_kernel");
-}
-
 // ------------------------------------------------------------------ host
 template <bool kBf16, bool kSplit, bool kEmbedded, int kCg, int kTrain = 0>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
@@ -1456,9 +1085,6 @@ int field_forward_tc(const void* packed, int precision, const float* rays, const
   p.n_points = (long long)n_rays * n_samples;
   p.sigma_only = sigma_only;
   p.out = raw;
-  // single-product bf16: the two-tiles-per-weight-pass kernel (SNB_BF16_PP=0 keeps the single-tile one for A/B runs)
-  static const bool use_pp = !(getenv("SNB_BF16_PP") && atoi(getenv("SNB_BF16_PP")) == 0);
-  if (precision == SNB_PREC_BF16 && use_pp) return launch_pp(p, st);
   return dispatch_tc<false>(precision, p, st);
 }
 

@@ -424,49 +424,3 @@ def test_fp16_training_storage_matches_fp32_storage_and_oracle(weights, n_rays, 
                 tol_o = 1e-3 if (train_noise or weights == "room") else 2e-3
                 assert rel_l2(got[k], v.grad) <= tol_o, (k, rel_l2(got[k], v.grad))
         print(f"fp16 training storage vs oracle autograd: worst rel-L2 {worst_o:.2e}", file=sys.stderr)
-
-
-# ------------------------------------------------------------------------------------------ bf16 two-tile kernel
-_PP_SCRIPT = r"""
-import sys, torch
-sys.path.insert(0, {root!r})
-from oracle import render_oracle as orc
-from sinnerf_b200 import synthetic
-from sinnerf_b200.nerf import NeRF, Embedding
-from sinnerf_b200.rendering import render_rays
-dev = "cuda:0"
-models = []
-for seed in (0, 1):
-    m = NeRF(use_new_activation=True); m.load_state_dict(orc.default_init_params(seed)); models.append(m.to(dev))
-emb = [Embedding(3, 10), Embedding(3, 4)]
-out = {{}}
-for n in (1, 130, 777, 5292):
-    rays = synthetic.random_rays("llff", n, seed=n).to(dev)
-    with torch.no_grad():
-        o = render_rays(models, emb, rays, 64, False, 0, 0, 64, 32768, False, precision="bf16")
-        tt = render_rays(models, emb, rays, 64, False, 0, 0, 64, 32768, False, precision="bf16", test_time=True)
-    out[n] = {{k: v.cpu() for k, v in o.items()}}
-    out[n]["tt_opacity_coarse"] = tt["opacity_coarse"].cpu()
-torch.save(out, sys.argv[1])
-"""
-
-
-def test_bf16_two_tile_kernel_matches_single_tile_kernel(tmp_path):
-    """SNB_PREC_BF16 inference runs field_pp_kernel (two 128-point tiles per CTA and weight pass); SNB_BF16_PP=0 keeps the
-    single-tile field_tc_kernel<bf16>.  Same products, same bf16 roundings: the two must agree to fp32 rounding of the
-    head dot products, at ragged sizes (1 / 130 / 777 rays) and at the configs[2] patch size, incl. the sigma-only pass."""
-    import os
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    script = tmp_path / "pp.py"
-    script.write_text(_PP_SCRIPT.format(root=root))
-    outs = {}
-    for flag in ("1", "0"):
-        path = tmp_path / f"o{flag}.pt"
-        env = dict(os.environ, SNB_BF16_PP=flag)
-        subprocess.run([sys.executable, str(script), str(path)], check=True, env=env, timeout=600)
-        outs[flag] = torch.load(path)
-    for n in outs["1"]:
-        for k in outs["1"][n]:
-            a, b = outs["1"][n][k], outs["0"][n][k]
-            assert rel_l2(a, b) <= 2e-5, (n, k, rel_l2(a, b))

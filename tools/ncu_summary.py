@@ -36,7 +36,7 @@ src = list(csv.reader(io.StringIO(run(["--page", "source", "--csv"]))))
 if len(src) > 2:
     h = src[1]
     ix = {k: i for i, k in enumerate(h)}
-    data = [r for r in src[2:] if len(r) == len(h)]
+    data = [r for r in src[2:] if len(r) == len(h) and r[ix["# Samples"]].strip().isdigit()]
     stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
     tot = sum(int(r[ix["# Samples"]]) for r in data) or 1
     print(f"== warp-stall samples: {tot}; top instructions")
