@@ -66,7 +66,8 @@ constexpr int kTile = 128;             // points per CTA tile (MMA M = 128 * cta
 constexpr int kNh = 128;               // output columns per MMA (N); a 256-wide layer is two halves
 constexpr int kEpiWarps = 16;          // warps 0..15: prologue / epilogue (4 per TMEM lane quadrant)
 constexpr int kMmaWarp = 16, kLoadWarp = 17;
-constexpr int kThreads = 576;          // <= 113 registers per thread
+constexpr int kEncWarp0 = 18, kEncWarps = 2;   // positional encodings of the NEXT slot, off the epilogue warps' critical path
+constexpr int kThreads = (kEncWarp0 + kEncWarps) * 32;   // 640: <= 102 registers per thread (96 used)
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
 
 // per cta_group geometry: a chunk is 128 output rows x (16 * steps) of K, steps <= kMaxSteps; each
@@ -327,6 +328,19 @@ __device__ __forceinline__ float softplus_fast(float s) {
   return fmaf(__log2f(1.0f + t), 0.6931471805599453f, fmaxf(s, 0.0f));   // max(s,0) + log1p(t)  (lg2.approx)
 }
 
+// sin / cos for the positional encoding of the single-product bf16 mode: two-constant Cody-Waite reduction to
+// [-pi, pi] and the MUFU approximations (abs error ~1e-6 for |x| up to ~1e4 -- three orders below bf16's 2^-9
+// rounding of the encoded value), ~8 instructions instead of sincosf's ~50.  In that mode an MMA phase is only 512
+// cycles and the encoding, done by the epilogue warps between layers, was on the critical path: 8.8k of a 32k-cycle
+// slot (profiles/r02_trace_bf16_before_fast_trig.txt).  The fp32-parity modes keep the accurate sincosf.
+__device__ __forceinline__ void sincos_fast(float x, float* sn, float* cs) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, x);
+  r = fmaf(k, 1.7484555e-7f, r);
+  *sn = __sinf(r);
+  *cs = __cosf(r);
+}
+
 // ------------------------------------------------------------------ pack kernel
 using ParamPtrsTc = ParamPtrs;
 
@@ -446,13 +460,15 @@ struct TcSmem {
   alignas(128) unsigned char dir[kParts][kTile * kDirPad * 2];
   alignas(16) float cst[kConstFloats];
   float sigp[4][kTile];           // sigma head partial sums per 32-column group; [0] ends up holding sigma
-  // (the rgb head's partial sums alias dir[0], idle by then: float [4][3][kTile])
   // training forward: per-warp 32 x 16 transposition tiles (row stride 20 words: conflict-free 128-bit
   // accesses) so the activations leave as 64 contiguous bytes per 4 lanes instead of 16 bytes per lane
   // at a 1 KB stride -- 8 lines per store instruction instead of 32
   alignas(16) float store_tile[kTrain == 1 ? kEpiWarps : 1][kTrain == 1 ? 32 : 1][20];
   uint64_t full[16], empty[16];
+  // (the rgb head's partial sums alias dir[0], idle by then: float [4][3][kTile])
   uint64_t d_full[2], a_ready[4], a_free, enc_ready, dir_ready, d_drained;
+  uint64_t enc_free, dir_free;    // MMA -> encoder warps: the last MMA reading enc / dir of this slot has retired
+  uint64_t rgb_done;              // epilogue -> encoder warps: the rgb partial sums parked in dir[0] have been consumed
   uint32_t tmem_base;
 };
 
@@ -527,9 +543,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], (kCg == 2 && leader) ? 2 : 1); mbar_init(&s.empty[i], 1); }
     mbar_init(&s.d_full[0], 1); mbar_init(&s.d_full[1], 1); mbar_init(&s.a_free, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&s.a_ready[i], kEpiWarps * 16 * kCg);   // the two warps-of-four that own the quarter
-    mbar_init(&s.enc_ready, kEpiWarps * 32 * kCg);
-    mbar_init(&s.dir_ready, kEpiWarps * 32 * kCg);
+    mbar_init(&s.enc_ready, kEncWarps * 32 * kCg);
+    mbar_init(&s.dir_ready, kEncWarps * 32 * kCg);
     mbar_init(&s.d_drained, kEpiWarps * 32 * kCg);
+    mbar_init(&s.enc_free, 1);
+    mbar_init(&s.dir_free, 1);
+    mbar_init(&s.rgb_done, kEpiWarps);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { if (kCg == 2) tmem_alloc_pair(&s.tmem_base); else tmem_alloc<512>(&s.tmem_base); }
@@ -538,6 +557,53 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   if (kCg == 2) cluster_sync_all();   // the peer's barriers exist before anyone signals them
   tc_fence_after();
   const uint32_t tbase = s.tmem_base;
+
+  // ---- helpers shared by the encoder and the epilogue warps
+  auto tile_of = [&](long long slot) { return (group + slot * n_groups) * kCg + cta_rank; };
+  // hand-off to the MMA issuer, which lives in the leader CTA
+  auto signal = [&](uint64_t* bar) { if (kCg == 2 && !leader) mbar_arrive_remote(bar, 0); else mbar_arrive(bar); };
+  // 16-bit storage: 8 consecutive features of one point -> one 16-byte cell of a T32 tensor
+  auto store_cell16 = [&](unsigned char* base, long long pt, int f8, int F, const float (&v)[8]) {
+    if (pt >= p.ppad) return;
+    const bool live = pt < p.n_points;
+    uint4 c;
+    c.x = live ? pack_half2_sat(v[0], v[1]) : 0u; c.y = live ? pack_half2_sat(v[2], v[3]) : 0u;
+    c.z = live ? pack_half2_sat(v[4], v[5]) : 0u; c.w = live ? pack_half2_sat(v[6], v[7]) : 0u;
+    *reinterpret_cast<uint4*>(base + a16_cell(pt, f8, F)) = c;
+  };
+  // 8 consecutive channels (one 16-byte core-matrix row of tile row `r`) -> hi (and lo) vector stores, canonical layout
+  auto put8 = [&](unsigned char* hi_base, unsigned char* lo_base, int k8, int r, const float (&v)[8]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_pair<kBf16, kSplit>(v[2 * j], v[2 * j + 1], h[j], l[j]);
+    const uint32_t off = (uint32_t)k8 * (kTile * 16) + r * 16;
+    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (kSplit) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  };
+  // 8 consecutive channels [c_lo, c_lo+8) of Embedding(3, L)(x): [x(3), sin(2^0 x)(3), cos(2^0 x)(3),
+  // sin(2^1 x)(3), ...] (nerf.py:36-41), one sincos per (frequency, coordinate) that the window touches
+  auto embed8 = [&](const float (&x)[3], int c_lo, int n_ch, int n_freqs, float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c_lo + j < 3) ? x[(c_lo + j) % 3] : 0.f;   // identity / zero pad
+    for (int f = 0; f < n_freqs; ++f) {
+      const int base = 3 + 6 * f;
+      if (base + 6 <= c_lo || base >= c_lo + 8) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int js = base + c - c_lo, jc = js + 3;
+        if ((js >= 0 && js < 8) || (jc >= 0 && jc < 8)) {
+          float sn, cs;
+          if (kSplit) sincosf(x[c] * (float)(1 << f), &sn, &cs);
+          else sincos_fast(x[c] * (float)(1 << f), &sn, &cs);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {           // static indices keep v[] in registers
+            if (j == js) v[j] = sn;
+            if (j == jc && base + 3 + c < n_ch) v[j] = cs;
+          }
+        }
+      }
+    }
+  };
 
   if (warp == kLoadWarp) {
     // ======================= weight loader (one elected lane) =======================
@@ -678,6 +744,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           if (c.commit & COMMIT_AFREE) commit(&s.a_free);
           if (c.commit & COMMIT_D0) commit(&s.d_full[0]);
           if (c.commit & COMMIT_D1) commit(&s.d_full[1]);
+          if (c.src == SRC_ENC && c.layer == 4 && c.half == 1) commit(&s.enc_free);   // last reader of enc in this slot
+          if (c.src == SRC_DIR) commit(&s.dir_free);
           trace(tr, 512 + CI * 4 + 3);
           if (++st == kStages) { st = 0; ph_full ^= 1; }
           trace(tr, CI * 4 + 3);
@@ -693,13 +761,106 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       }
     }
     __syncwarp();
+  } else if (warp >= kEncWarp0) {
+    // ======================= encoder warps: positional encodings of the NEXT slot =======================
+    // 64 threads, two tile rows each.  In round 1 the epilogue warps did this in their idle windows; in the
+    // single-product bf16 mode (512-cycle MMA phases) those windows do not exist and the encodings -- global loads of
+    // the ray and depth, a 64-bit division, 30 sin/cos pairs -- sat on the layer-to-layer critical path: ~8k of a
+    // 30k-cycle slot (profiles/r02_trace_bf16_fast_trig.txt).  Here they run beside everything else: xyz for slot s+1
+    // as soon as the skip layer of slot s has consumed enc (enc_free), dir as soon as the direction layer has (dir_free).
+    const int e = (warp - kEncWarp0) * 32 + lane;
+    auto encode_rows = [&](long long slot, bool xyz) {
+#pragma unroll 1
+      for (int rr = 0; rr < kTile / (kEncWarps * 32); ++rr) {
+        const int r = e + rr * (kEncWarps * 32);
+        const long long pt = tile_of(slot) * kTile + r;
+        const bool live = pt < p.n_points;
+        float x[3] = {0.f, 0.f, 0.f};
+        const float* xr = nullptr;
+        if (kEmbedded) {
+          xr = p.x + pt * p.x_stride;
+        } else if (live) {
+          const long long ray = pt / p.n_samples;
+          const float4 r0 = *reinterpret_cast<const float4*>(p.rays + ray * 8);
+          const float4 r1 = *reinterpret_cast<const float4*>(p.rays + ray * 8 + 4);
+          if (xyz) {
+            const float zz = p.z[pt];
+            x[0] = __fadd_rn(r0.x, __fmul_rn(r0.w, zz));   // rendering.py:284-285 rounding
+            x[1] = __fadd_rn(r0.y, __fmul_rn(r1.x, zz));
+            x[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, zz));
+          } else {
+            x[0] = r0.w; x[1] = r1.x; x[2] = r1.y;          // ray direction (not normalised, rendering.py:261)
+          }
+        }
+        // all channels of the row in registers, one sin / cos pair per (frequency, coordinate): static indices only
+        auto emit = [&](auto ktag, const float (&v8)[8]) {
+          constexpr int k8 = decltype(ktag)::value;
+          if (!kEmbedded) {
+            if (kTrain == 1 && live) {
+              float4* dst = reinterpret_cast<float4*>((xyz ? p.save_enc + pt * kXyzPad : p.save_dir + pt * kDirPad) + k8 * 8);
+              dst[0] = make_float4(v8[0], v8[1], v8[2], v8[3]); dst[1] = make_float4(v8[4], v8[5], v8[6], v8[7]);
+            }
+            if (kTrain == 2) store_cell16(xyz ? p.a_enc : p.a_dir, pt, k8, xyz ? kXyzPad : kDirPad, v8);
+          }
+          if (xyz) put8(s.enc[0], s.enc[kSplit ? 1 : 0], k8, r, v8);
+          else put8(s.dir[0], s.dir[kSplit ? 1 : 0], k8, r, v8);
+        };
+        auto encode_all = [&](auto ltag) {
+          constexpr int L = decltype(ltag)::value;            // 10 (xyz, 63 -> 64 channels) or 4 (dir, 27 -> 32)
+          constexpr int kCh = 3 * (2 * L + 1), kPad = (kCh + 7) / 8 * 8;
+          float v[kPad];
+#pragma unroll
+          for (int j = 0; j < kPad; ++j) v[j] = 0.f;
+          if (kEmbedded) {
+            const int nin = p.sigma_only ? kXyzCh : kXyzCh + kDirCh;
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) {
+              const int col = L == SNB_XYZ_FREQS ? j : kXyzCh + j;
+              v[j] = (live && col < nin) ? xr[col] : 0.f;
+            }
+          } else {
+            v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
+#pragma unroll
+            for (int f = 0; f < L; ++f)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                float sn, cs;
+                if (kSplit) sincosf(x[c] * (float)(1 << f), &sn, &cs);
+                else sincos_fast(x[c] * (float)(1 << f), &sn, &cs);
+                v[3 + 6 * f + c] = sn;
+                v[3 + 6 * f + 3 + c] = cs;
+              }
+          }
+          static_for<kPad / 8>([&](auto ktag) {
+            constexpr int k8 = decltype(ktag)::value;
+            const float v8[8] = {v[8 * k8], v[8 * k8 + 1], v[8 * k8 + 2], v[8 * k8 + 3], v[8 * k8 + 4], v[8 * k8 + 5], v[8 * k8 + 6], v[8 * k8 + 7]};
+            emit(ktag, v8);
+          });
+        };
+        if (xyz) encode_all(std::integral_constant<int, SNB_XYZ_FREQS>{});
+        else encode_all(std::integral_constant<int, SNB_DIR_FREQS>{});
+      }
+      fence_proxy_async_smem();     // generic-proxy smem writes -> visible to tcgen05.mma
+      signal(xyz ? &s.enc_ready : &s.dir_ready);
+    };
+    if (n_slots > 0) {
+      encode_rows(0, true);
+      if (!p.sigma_only) encode_rows(0, false);
+    }
+    for (long long slot = 0; slot + 1 < n_slots; ++slot) {
+      mbar_wait(&s.enc_free, (uint32_t)slot & 1);
+      encode_rows(slot + 1, true);
+      if (!p.sigma_only) {
+        mbar_wait(&s.dir_free, (uint32_t)slot & 1);
+        mbar_wait(&s.rgb_done, (uint32_t)slot & 1);
+        encode_rows(slot + 1, false);
+      }
+    }
   } else {
     // ======================= prologue / epilogue warps =======================
     const int quad = warp & 3, ch = warp >> 2;       // TMEM lane quadrant, 32-column group (0..3) of a 128-column half
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    // hand-off to the MMA issuer, which lives in the leader CTA
-    auto signal = [&](uint64_t* bar) { if (kCg == 2 && !leader) mbar_arrive_remote(bar, 0); else mbar_arrive(bar); };
     uint32_t ph_d = 0, ph_free = 0;       // ph_d: bit h = parity of d_full[h]
     // training forward: 16 consecutive columns of this warp's 32 rows -> global, through the warp's tile.
     // `x4[k]` = this thread's row, columns [4k, 4k+4); dst_block = address of (first row of the block, first column)
@@ -717,117 +878,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       }
     };
 
-    // 16-bit storage: 8 consecutive features of this thread's point -> one 16-byte cell of a T32 tensor; the 32
-    // lanes of the warp are 32 consecutive points, so a store instruction covers 512 contiguous bytes
-    auto store_cell16 = [&](unsigned char* base, long long pt, int f8, int F, const float (&v)[8]) {
-      if (pt >= p.ppad) return;
-      const bool live = pt < p.n_points;
-      uint4 c;
-      c.x = live ? pack_half2_sat(v[0], v[1]) : 0u; c.y = live ? pack_half2_sat(v[2], v[3]) : 0u;
-      c.z = live ? pack_half2_sat(v[4], v[5]) : 0u; c.w = live ? pack_half2_sat(v[6], v[7]) : 0u;
-      *reinterpret_cast<uint4*>(base + a16_cell(pt, f8, F)) = c;
-    };
-
-    // ---- positional encodings of one tile -> smem (canonical, hi/lo).  Split in pieces so they
-    // fit the epilogue warps' idle windows: xyz part 0 (identity + 3 of this thread's 5
-    // frequencies), xyz part 1 (the other 2 + zero pad), and the direction embedding.
-    // 8 consecutive channels (one 16-byte core-matrix row) -> hi (and lo) vector stores
-    auto put8 = [&](unsigned char* hi_base, unsigned char* lo_base, int k8, const float (&v)[8]) {
-      uint32_t h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) split_pair<kBf16, kSplit>(v[2 * j], v[2 * j + 1], h[j], l[j]);
-      const uint32_t off = (uint32_t)k8 * (kTile * 16) + row * 16;
-      *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
-      if (kSplit) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
-    };
-    auto tile_of = [&](long long slot) { return (group + slot * n_groups) * kCg + cta_rank; };
-    // 8 consecutive channels [c_lo, c_lo+8) of Embedding(3, L)(x): [x(3), sin(2^0 x)(3), cos(2^0 x)(3),
-    // sin(2^1 x)(3), ...] (nerf.py:36-41), one sincosf per (frequency, coordinate) that the window touches
-    auto embed8 = [&](const float (&x)[3], int c_lo, int n_ch, int n_freqs, float (&v)[8]) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (c_lo + j < 3) ? x[(c_lo + j) % 3] : 0.f;   // identity / zero pad
-      for (int f = 0; f < n_freqs; ++f) {
-        const int base = 3 + 6 * f;
-        if (base + 6 <= c_lo || base >= c_lo + 8) continue;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int js = base + c - c_lo, jc = js + 3;
-          if ((js >= 0 && js < 8) || (jc >= 0 && jc < 8)) {
-            float sn, cs;
-            sincosf(x[c] * (float)(1 << f), &sn, &cs);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {           // static indices keep v[] in registers
-              if (j == js) v[j] = sn;
-              if (j == jc && base + 3 + c < n_ch) v[j] = cs;
-            }
-          }
-        }
-      }
-    };
-    // xyz embedding of one tile: this thread writes 16 of the 64 channels of its row, in two parts of 8
-    // (so the work can be spread over two idle windows)
-    auto encode_xyz = [&](long long slot, int part) {
-      const long long pt = tile_of(slot) * kTile + row;
-      const int c_lo = (ch * 2 + part) * 8;
-      float v[8];
-      if (kEmbedded) {
-        const float* xr = p.x + pt * p.x_stride;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (pt < p.n_points && c_lo + j < kXyzCh) ? xr[c_lo + j] : 0.f;
-      } else {
-        float x[3] = {0.f, 0.f, 0.f};
-        if (pt < p.n_points) {
-          const long long ray = pt / p.n_samples;
-          const float4 r0 = *reinterpret_cast<const float4*>(p.rays + ray * 8);
-          const float4 r1 = *reinterpret_cast<const float4*>(p.rays + ray * 8 + 4);
-          const float zz = p.z[pt];
-          x[0] = __fadd_rn(r0.x, __fmul_rn(r0.w, zz));   // rendering.py:284-285 rounding
-          x[1] = __fadd_rn(r0.y, __fmul_rn(r1.x, zz));
-          x[2] = __fadd_rn(r0.z, __fmul_rn(r1.y, zz));
-        }
-        embed8(x, c_lo, kXyzCh, SNB_XYZ_FREQS, v);
-        if (kTrain == 1 && pt < p.n_points) {
-          float4* dst = reinterpret_cast<float4*>(p.save_enc + pt * kXyzPad + c_lo);
-          dst[0] = make_float4(v[0], v[1], v[2], v[3]); dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (kTrain == 2) store_cell16(p.a_enc, pt, c_lo >> 3, kXyzPad, v);
-      }
-      put8(s.enc[0], s.enc[kSplit ? 1 : 0], c_lo / 8, v);
-      if (part == 1) {
-        fence_proxy_async_smem();     // generic-proxy smem writes -> visible to tcgen05.mma
-        signal(&s.enc_ready);
-      }
-    };
-    auto encode_dir = [&](long long slot) {
-      const long long pt = tile_of(slot) * kTile + row;
-      const int c_lo = ch * 8;
-      float v[8];
-      if (kEmbedded) {
-        const int nin = p.sigma_only ? kXyzCh : kXyzCh + kDirCh;
-        const float* xr = p.x + pt * p.x_stride;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          v[j] = (pt < p.n_points && c_lo + j < kDirCh && kXyzCh + c_lo + j < nin) ? xr[kXyzCh + c_lo + j] : 0.f;
-      } else {
-        float d[3] = {0.f, 0.f, 0.f};
-        if (pt < p.n_points) {
-          const long long ray = pt / p.n_samples;
-          d[0] = p.rays[ray * 8 + 3]; d[1] = p.rays[ray * 8 + 4]; d[2] = p.rays[ray * 8 + 5];
-        }
-        embed8(d, c_lo, kDirCh, SNB_DIR_FREQS, v);
-        if (kTrain == 1 && pt < p.n_points) {
-          float4* dst = reinterpret_cast<float4*>(p.save_dir + pt * kDirPad + c_lo);
-          dst[0] = make_float4(v[0], v[1], v[2], v[3]); dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (kTrain == 2) store_cell16(p.a_dir, pt, c_lo >> 3, kDirPad, v);
-      }
-      put8(s.dir[0], s.dir[kSplit ? 1 : 0], c_lo / 8, v);
-      fence_proxy_async_smem();
-      signal(&s.dir_ready);
-    };
-
-    // first slot: nothing to hide behind
-    if (n_slots > 0) { encode_xyz(0, 0); encode_xyz(0, 1); }
 
     for (long long slot = 0; slot < n_slots; ++slot) {
       const long long pt = tile_of(slot) * kTile + row;
@@ -931,9 +981,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           }
         }
         // ---- background work in the idle window before this layer's next accumulator half is ready
-        if (l == 0 && !p.sigma_only) encode_dir(slot);                       // dir layer of THIS slot
-        if (l == 5 && slot + 1 < n_slots) encode_xyz(slot + 1, 0);            // enc is free once layer 5's
-        if (l == 6 && slot + 1 < n_slots) encode_xyz(slot + 1, 1);            // (skip) MMAs have retired
         if (l == 7) {
           // sigma head (nerf.py:136): combine the two column halves of each row
           s.sigp[ch][row] = sig_part;
@@ -1004,8 +1051,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
                 live ? make_uint4(g16[4 * c], g16[4 * c + 1], g16[4 * c + 2], g16[4 * c + 3]) : make_uint4(0u, 0u, 0u, 0u);
         }
         trace(tr, tb + 3);
-        // rgb partial sums go through the dir-embedding buffer: its last readers (this slot's dir-layer
-        // MMAs) have retired, and the next slot's encode_dir runs after the barrier below
+        // rgb partial sums go through the dir-embedding buffer: its last readers (this slot's dir-layer MMAs) have
+        // retired, and the encoder warps write the next slot's dir embedding only after rgb_done below
         float* rgbp = reinterpret_cast<float*>(s.dir[0]);     // [4][3][kTile]
         rgbp[(ch * 3 + 0) * kTile + row] = a0; rgbp[(ch * 3 + 1) * kTile + row] = a1; rgbp[(ch * 3 + 2) * kTile + row] = a2;
         epi_bar_sync();
@@ -1020,6 +1067,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           reinterpret_cast<float4*>(p.out)[pt] = make_float4(c[0], c[1], c[2], s.sigp[0][row]);
         }
         epi_bar_sync();
+        if (lane == 0) mbar_arrive(&s.rgb_done);
         trace(tr, tb + 4);
       }
     }
