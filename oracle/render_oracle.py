@@ -69,13 +69,21 @@ def widened_sigmoid(x: Tensor) -> Tensor:
 # --------------------------------------------------------------------------- #
 # a-6  the 8x256 field MLP                                                     #
 # --------------------------------------------------------------------------- #
-def _affine(p: Params, name: str, x: Tensor) -> Tensor:
-    return torch.addmm(p[name + ".bias"], x, p[name + ".weight"].t())
+def _round_st(x: Tensor, dt) -> Tensor:
+    """x rounded to dtype `dt` in the forward, identity in the backward (None: x itself)."""
+    return x if dt is None else x + (x.to(dt).to(x.dtype) - x).detach()
+
+
+def _affine(p: Params, name: str, x: Tensor, linear_dtype=None) -> Tensor:
+    """nn.Linear.  linear_dtype (e.g. torch.bfloat16): BOTH operands rounded to it, fp32 accumulate -- the arithmetic
+    of the product's reduced-precision modes (the reference itself has no such path; SURVEY 8c defines the bf16
+    configuration as 'nn.Linear in half precision, everything else fp32', i.e. autocast)."""
+    return torch.addmm(p[name + ".bias"], _round_st(x, linear_dtype), _round_st(p[name + ".weight"], linear_dtype).t())
 
 
 def field_mlp(p: Params, xyz_enc: Tensor, dir_enc: Optional[Tensor],
               sigma_only: bool = False, new_activation: bool = True,
-              depth: int = 8, skips=(4,)) -> Tensor:
+              depth: int = 8, skips=(4,), linear_dtype=None, fold_bottleneck: bool = False) -> Tensor:
     """models/nerf.py:105-148.
 
     xyz_enc (P,63), dir_enc (P,27) -> (P,4) = [r,g,b,sigma]  (or (P,1) sigma).
@@ -87,12 +95,23 @@ def field_mlp(p: Params, xyz_enc: Tensor, dir_enc: Optional[Tensor],
     for i in range(depth):
         if i in skips:
             h = torch.cat([xyz_enc, h], dim=-1)
-        h = torch.relu_(_affine(p, f"xyz_encoding_{i + 1}.0", h))  # nn.ReLU(True), nerf.py:73
-    sigma = _affine(p, "sigma", h)
+        h = torch.relu_(_affine(p, f"xyz_encoding_{i + 1}.0", h, linear_dtype))  # nn.ReLU(True), nerf.py:73
+    sigma = _affine(p, "sigma", h)          # the heads are fp32 dot products in every mode
     if sigma_only:
         return sigma
-    feat = _affine(p, "xyz_encoding_final", h)
-    g = _affine(p, "dir_encoding.0", torch.cat([feat, dir_enc], dim=-1))
+    if fold_bottleneck:
+        # the product's tensor-core modes fold the activation-free bottleneck into the direction layer:
+        # Wd[:, :W] (Wf h + bf) = (Wd[:, :W] Wf) h + Wd[:, :W] bf, the product formed in fp64 and rounded once
+        Wd, bd = p["dir_encoding.0.weight"], p["dir_encoding.0.bias"]
+        Wf, bf = p["xyz_encoding_final.weight"], p["xyz_encoding_final.bias"]
+        w = h.shape[-1]
+        Wp = (Wd[:, :w].double() @ Wf.double()).to(h.dtype)
+        bp = bd + (Wd[:, :w].double() @ bf.double()).to(h.dtype)
+        g = bp + _round_st(h, linear_dtype) @ _round_st(Wp, linear_dtype).t() \
+            + _round_st(dir_enc, linear_dtype) @ _round_st(Wd[:, w:], linear_dtype).t()
+    else:
+        feat = _affine(p, "xyz_encoding_final", h, linear_dtype)
+        g = _affine(p, "dir_encoding.0", torch.cat([feat, dir_enc], dim=-1), linear_dtype)
     g = shifted_softplus(g) if new_activation else torch.relu(g)
     c = _affine(p, "rgb.0", g)
     c = widened_sigmoid(c) if new_activation else torch.sigmoid(c)
@@ -188,7 +207,8 @@ def sample_pdf(bins: Tensor, weights: Tensor, n_importance: int, det: bool = Fal
 # --------------------------------------------------------------------------- #
 def field_pass(p: Params, rays_o: Tensor, rays_d: Tensor, dir_enc: Tensor, z: Tensor,
                noise: Optional[Tensor], white_back: bool, weights_only: bool = False,
-               new_activation: bool = True, point_chunk: int = 1 << 15):
+               new_activation: bool = True, point_chunk: int = 1 << 15, linear_dtype=None,
+               fold_bottleneck: bool = False):
     """models/rendering.py:161-248 (the nested ``inference``) incl. the point
     generation at :284-285 / :317-318.  Returns a dict with raw (N,S,4) (or
     sigma (N,S)), rgb, depth, weights.
@@ -200,7 +220,8 @@ def field_pass(p: Params, rays_o: Tensor, rays_d: Tensor, dir_enc: Tensor, z: Te
     for i in range(0, xyz.shape[0], point_chunk):
         e = embed(xyz[i:i + point_chunk], N_XYZ_FREQS)
         outs.append(field_mlp(p, e, None if weights_only else dirs[i:i + point_chunk],
-                              sigma_only=weights_only, new_activation=new_activation))
+                              sigma_only=weights_only, new_activation=new_activation, linear_dtype=linear_dtype,
+                              fold_bottleneck=fold_bottleneck))
     raw = torch.cat(outs, dim=0)
     d_norm = torch.norm(rays_d.unsqueeze(1), dim=-1)
     if weights_only:
@@ -218,8 +239,12 @@ def render_rays(coarse: Params, fine: Optional[Params], rays: Tensor, N_samples:
                 use_disp: bool = False, perturb: float = 0.0, noise_std: float = 1.0,
                 N_importance: int = 0, white_back: bool = False, test_time: bool = False,
                 new_activation: bool = True, rng: Optional[Dict[str, Tensor]] = None,
-                z_fine_override: Optional[Tensor] = None, return_intermediates: bool = False):
+                z_fine_override: Optional[Tensor] = None, return_intermediates: bool = False,
+                linear_dtype=None, fold_bottleneck: bool = False):
     """models/rendering.py:126-335.
+
+    linear_dtype / fold_bottleneck (not in the reference): restate the product's reduced-precision MLP modes --
+    see _affine / field_mlp -- so that those modes have a tight oracle of their own.
 
     ``rng`` may hold the four random tensors the reference draws, in its order
     (SURVEY.md 8a): 'perturb_u' (N,Sc) rand, 'noise_coarse' (N,Sc) randn,
@@ -243,7 +268,8 @@ def render_rays(coarse: Params, fine: Optional[Params], rays: Tensor, N_samples:
         rng["noise_coarse"] = torch.randn(n, N_samples, device=rays.device)        # RNG call 2 (:224)
     noise_c = rng["noise_coarse"].to(rays.dtype) * noise_std
     c = field_pass(coarse, rays_o, rays_d, dir_enc, z, noise_c, white_back,
-                   weights_only=test_time, new_activation=new_activation)
+                   weights_only=test_time, new_activation=new_activation, linear_dtype=linear_dtype,
+                   fold_bottleneck=fold_bottleneck)
     out = {"opacity_coarse": c["weights"]}
     if not test_time:
         out["rgb_coarse"], out["depth_coarse"] = c["rgb"], c["depth"]
@@ -264,7 +290,7 @@ def render_rays(coarse: Params, fine: Optional[Params], rays: Tensor, N_samples:
             rng["noise_fine"] = torch.randn(n, N_samples + N_importance, device=rays.device)  # RNG call 4
         noise_f = rng["noise_fine"].to(rays.dtype) * noise_std
         f = field_pass(fine, rays_o, rays_d, dir_enc, z_f, noise_f, white_back,
-                       new_activation=new_activation)
+                       new_activation=new_activation, linear_dtype=linear_dtype, fold_bottleneck=fold_bottleneck)
         out["rgb_fine"], out["depth_fine"], out["opacity_fine"] = f["rgb"], f["depth"], f["weights"]
         inter.update(z_new=z_new, z_fine=z_f, raw_fine=f["raw"])
     else:
