@@ -211,8 +211,13 @@ int field_backward16(const float* const* params, float* const* grads, int new_ac
   const uint32_t* mask = reinterpret_cast<const uint32_t*>(act + A.mask);
   auto H = [&](int l) { return act + A.h[l]; };                          // l = 0..7: h1..h8
   auto M = [&](int l) { return mask + (size_t)l * 8 * (size_t)ppad; };   // ReLU mask of h_{l+1}
-  // SNB_BWD16_LO=0: hi-only gradient chain (2.5 KB per point and layer instead of 3; first-layer gradients ~1e-3)
-  static const bool use_lo = !(getenv("SNB_BWD16_LO") && atoi(getenv("SNB_BWD16_LO")) == 0);
+  // The gradient chain carries its fp16 rounding residual (a second plane) from dS down to dH_4; below that the
+  // chain is hi-only: a weight gradient then sees at most 4 chained 11-bit roundings (measured <= 4e-4 rel-L2, parity
+  // bar 1e-3) and the four lowest hops move 1 KB per point instead of 2.  SNB_BWD16_LO = 0: hi-only everywhere
+  // (first-layer gradients ~6e-4), 2: residual planes all the way down (~2.4e-4 flat).
+  static const int lo_mode = getenv("SNB_BWD16_LO") ? atoi(getenv("SNB_BWD16_LO")) : 1;
+  const bool use_lo = lo_mode != 0;
+  const int lo_floor = lo_mode == 2 ? 0 : 4;       // dH_l has a residual plane for l >= lo_floor
   int rc;
   if (cudaMemsetAsync(state, 0, kBwdStateFloats * sizeof(float), st) != cudaSuccess)
     return fail(SNB_ERR_CUDA, "field_backward16: cudaMemsetAsync failed");
@@ -273,8 +278,10 @@ int field_backward16(const float* const* params, float* const* grads, int new_ac
     } else {
       if ((rc = run_wgrad16(cur, 256, H(l - 1), 256, 256, grads[2 * l], ldw, 0, grads[2 * l + 1], sc, nullptr, nullptr, nullptr, ppad, st))) return rc;
     }
-    if ((rc = run_dgrad16(cur, cur_lo, 256, params[2 * l], ldw, l == 4 ? kXyzCh : 0, M(l - 1), nullptr, 0, nullptr, nxt, nxt_lo,
-                          state, ST_AMAX_H0 + l, ST_SCALE_H0 + l, ST_L1_L0 + l, ST_AMAX_H0 + l - 1, ST_SCALE_H0 + l - 1, P, st)))
+    const bool lo_in = use_lo && l >= lo_floor, lo_out = use_lo && l - 1 >= lo_floor;
+    if ((rc = run_dgrad16(cur, lo_in ? cur_lo : nullptr, 256, params[2 * l], ldw, l == 4 ? kXyzCh : 0, M(l - 1), nullptr, 0, nullptr,
+                          nxt, lo_out ? nxt_lo : nullptr, state, ST_AMAX_H0 + l, ST_SCALE_H0 + l, ST_L1_L0 + l, ST_AMAX_H0 + l - 1,
+                          ST_SCALE_H0 + l - 1, P, st)))
       return rc;
     unsigned char* t = cur; cur = nxt; nxt = t;
     t = cur_lo; cur_lo = nxt_lo; nxt_lo = t;

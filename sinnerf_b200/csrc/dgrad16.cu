@@ -72,8 +72,10 @@ __device__ __forceinline__ void f16_split_pair(float x0, float x1, uint32_t& hi,
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int NRED, bool kLo>
+// kLoIn: dY comes with its residual plane (3 products); kLoOut: dX is written with its residual plane
+template <int NRED, bool kLoIn, bool kLoOut>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad16_kernel(Dgrad16Args a) {
+  constexpr bool kLo = kLoIn;
   using S = Dg16Smem<NRED>;
   constexpr int kQ = NRED / 64;               // K quarters (64 reduction columns each)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -234,7 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
           tmem_ld32(tbase + lane_base + kDgColD + c0, v);
           tmem_wait_ld();
           if (g == 3) { tc_fence_before(); signal(&s.d_drained[h]); }   // half h is in registers
-          uint32_t o[16], ol[kLo ? 16 : 1];
+          uint32_t o[16], ol[kLoOut ? 16 : 1];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float2 e = *reinterpret_cast<const float2*>(s.evec + c0 + 2 * j);
@@ -244,7 +246,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
             x1 = (mw[g] >> (2 * j + 1)) & 1u ? x1 : 0.f;
             amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
             o[j] = pack_half2_sat(x0, x1);
-            if (kLo) {
+            if (kLoOut) {
               const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(&o[j]));
               ol[j] = pack_half2_sat(x0 - hv.x, x1 - hv.y);
             }
@@ -253,7 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
 #pragma unroll
             for (int c = 0; c < 4; ++c)
               *reinterpret_cast<uint4*>(a.dX + a16_cell(pt, (c0 >> 3) + c, 256)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-            if (kLo) {
+            if (kLoOut) {
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 *reinterpret_cast<uint4*>(a.dX_lo + a16_cell(pt, (c0 >> 3) + c, 256)) = make_uint4(ol[4 * c], ol[4 * c + 1], ol[4 * c + 2], ol[4 * c + 3]);
@@ -273,34 +275,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDgThreads, 1) dgrad
   if (warp == kDgMmaWarp) tmem_dealloc_pair(tbase);
 }
 
-template <int NRED, bool kLo>
+template <int NRED, bool kLoIn, bool kLoOut>
 int launch_dgrad16(const Dgrad16Args& a, cudaStream_t st) {
   static SmemOptIn optin;
   const int smem = (int)sizeof(Dg16Smem<NRED>) + 1024;
-  if (int rc = ensure_smem(dgrad16_kernel<NRED, kLo>, optin, smem, "dgrad16")) return rc;
+  if (int rc = ensure_smem(dgrad16_kernel<NRED, kLoIn, kLoOut>, optin, smem, "dgrad16")) return rc;
   const int sms = sm_count();
   const long long ntiles = (a.P + kDgTile - 1) / kDgTile;
   long long pairs = (ntiles + 1) / 2;
   if (pairs > sms / 2) pairs = sms / 2;
-  dgrad16_kernel<NRED, kLo><<<(unsigned)(2 * pairs), kDgThreads, smem, st>>>(a);
+  dgrad16_kernel<NRED, kLoIn, kLoOut><<<(unsigned)(2 * pairs), kDgThreads, smem, st>>>(a);
   return check_launch("dgrad16_kernel");
 }
 
 }  // namespace
 
 // dY (Ppad, N) -> dX (Ppad, 256), fp16 T32 hi (+ lo) planes; scales and running maxima live in `state` (act16.cuh).
-// dY_lo / dX_lo both NULL = the hi-only variant.
+// dY_lo / dX_lo NULL = that tensor has no residual plane (hi-only).
 int run_dgrad16(const void* dY, const void* dY_lo, int N, const float* W, int ldw, int col_off, const uint32_t* mask,
                 const float* extra, int extra_stride, const float* evec, void* dX, void* dX_lo, float* state, int st_amax_in,
                 int st_scale_in, int st_l1, int st_amax_out, int st_scale_out, long long P, cudaStream_t st) {
   if (P == 0) return SNB_OK;
-  if ((dY_lo == nullptr) != (dX_lo == nullptr)) return fail(SNB_ERR_INVALID, "run_dgrad16: lo planes must be given for both tensors or none");
   Dgrad16Args a{reinterpret_cast<const unsigned char*>(dY), reinterpret_cast<const unsigned char*>(dY_lo), W, ldw, col_off, mask,
                 extra, extra_stride, evec, reinterpret_cast<unsigned char*>(dX), reinterpret_cast<unsigned char*>(dX_lo), state,
                 st_amax_in, st_scale_in, st_l1, st_amax_out, st_scale_out, P, a16_pad(P)};
-  const bool lo = dY_lo != nullptr;
-  if (N == 256) return lo ? launch_dgrad16<256, true>(a, st) : launch_dgrad16<256, false>(a, st);
-  if (N == 128) return lo ? launch_dgrad16<128, true>(a, st) : launch_dgrad16<128, false>(a, st);
+  const bool li = dY_lo != nullptr, lo = dX_lo != nullptr;
+  if (N == 256) {
+    if (li && lo) return launch_dgrad16<256, true, true>(a, st);
+    if (li) return launch_dgrad16<256, true, false>(a, st);
+    if (!lo) return launch_dgrad16<256, false, false>(a, st);
+  }
+  if (N == 128) {
+    if (li && lo) return launch_dgrad16<128, true, true>(a, st);
+    if (!li && !lo) return launch_dgrad16<128, false, false>(a, st);
+  }
+  if (!li && lo) return fail(SNB_ERR_INVALID, "run_dgrad16: a residual plane cannot be produced from a hi-only input chain");
   return fail(SNB_ERR_INVALID, "run_dgrad16: unsupported reduction length %d", N);
 }
 
