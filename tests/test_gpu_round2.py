@@ -405,7 +405,7 @@ def test_fp16_training_storage_matches_fp32_storage_and_oracle(weights, n_rays, 
                 worst, worst_k = rel_l2(a[k], b[k]), k
             assert rel_l2(a[k], b[k]) <= 1e-3, (k, rel_l2(a[k], b[k]))
     print(f"fp16 vs fp32 training storage ({weights}, {n_rays} rays, noise={train_noise}): worst rel-L2 {worst:.2e} ({worst_k})", file=sys.stderr)
-    if n_rays <= 256:
+    if True:      # also at 1 500 rays (288 000 points, several tiles per CTA): ~10 s of CPU autograd
         oc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
         of = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
         ref = orc.render_rays(oc, of, rays, N_samples=64, N_importance=64, perturb=perturb, noise_std=noise_std, rng=rng,
