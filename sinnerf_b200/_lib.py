@@ -11,7 +11,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsinnerf_b200.so")
+# SNB_LIB_PATH: load another build of the same library (A/B timing of kernel variants by the tools/ scripts)
+LIB_PATH = os.environ.get("SNB_LIB_PATH") or os.path.join(_PKG, "libsinnerf_b200.so")
 
 SNB_OK = 0
 PRECISIONS = {"fp32": 0, "f16x3": 1, "bf16x3": 2, "bf16": 3}

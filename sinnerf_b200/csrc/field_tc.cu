@@ -328,6 +328,38 @@ __device__ __forceinline__ float softplus_fast(float s) {
   return fmaf(__log2f(1.0f + t), 0.6931471805599453f, fmaxf(s, 0.0f));   // max(s,0) + log1p(t)  (lg2.approx)
 }
 
+// One-MUFU variant: log1p(t) on (0, 1] as t * q(t), q a minimax polynomial (degree 7: max abs error 2.5e-7 evaluated
+// in fp32 -- the rounding level of the O(1) result; degree 4 for the single-product mode: 4e-5, three orders below the
+// bf16 rounding of that mode's operands).  The direction-layer epilogue is 128 softplus per point and was MUFU-bound
+// (2 MUFU each, 16 lanes/clk/SM = 2048 cycles per tile); the FMA pipe has the room (8 resp. 5 FMAs).
+template <bool kLowPrec>
+__device__ __forceinline__ float softplus_poly(float s) {
+  float t;                                                             // exp(-|s|) in (0, 1]
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * fabsf(s)));
+  float q;
+  if (kLowPrec) {
+    q = fmaf(0.04155111312866211f, t, -0.157838374376297f);
+    q = fmaf(q, t, 0.30656111240386963f);
+    q = fmaf(q, t, -0.4970308542251587f);
+    q = fmaf(q, t, 0.9999449849128723f);
+  } else {
+    q = fmaf(-0.008574675768613815f, t, 0.044214192777872086f);
+    q = fmaf(q, t, -0.10785368084907532f);
+    q = fmaf(q, t, 0.17757023870944977f);
+    q = fmaf(q, t, -0.2449961155653f);
+    q = fmaf(q, t, 0.3327617645263672f);
+    q = fmaf(q, t, -0.49997448921203613f);
+    q = fmaf(q, t, 0.9999998211860657f);
+  }
+  return fmaf(q, t, fmaxf(s, 0.0f));
+}
+#ifndef SNB_ROTATE
+#define SNB_ROTATE 0
+#endif
+#ifndef SNB_SOFTPLUS_POLY
+#define SNB_SOFTPLUS_POLY 0
+#endif
+
 // sin / cos for the positional encoding of the single-product bf16 mode: two-constant Cody-Waite reduction to
 // [-pi, pi] and the MUFU approximations (abs error ~1e-6 for |x| up to ~1e4 -- three orders below bf16's 2^-9
 // rounding of the encoded value), ~8 instructions instead of sincosf's ~50.  In that mode an MMA phase is only 512
@@ -460,6 +492,9 @@ struct TcSmem {
   alignas(128) unsigned char dir[kParts][kTile * kDirPad * 2];
   alignas(16) float cst[kConstFloats];
   float sigp[4][kTile];           // sigma head partial sums per 32-column group; [0] ends up holding sigma
+  // rgb head partial sums [4][3][kTile].  The split modes have no room for them and alias dir[0] (idle by then); the
+  // single-product mode has, which lets the encoder warps write the next dir embedding without waiting for rgb_done
+  float rgbp_own[kSplit ? 1 : 12 * kTile];
   // training forward: per-warp 32 x 16 transposition tiles (row stride 20 words: conflict-free 128-bit
   // accesses) so the activations leave as 64 contiguous bytes per 4 lanes instead of 16 bytes per lane
   // at a 1 KB stride -- 8 lines per store instruction instead of 32
@@ -469,6 +504,9 @@ struct TcSmem {
   uint64_t d_full[2], a_ready[4], a_free, enc_ready, dir_ready, d_drained;
   uint64_t enc_free, dir_free;    // MMA -> encoder warps: the last MMA reading enc / dir of this slot has retired
   uint64_t rgb_done;              // epilogue -> encoder warps: the rgb partial sums parked in dir[0] have been consumed
+  uint64_t d_full_dir;            // single-product mode: the direction layer's own "accumulator full" (without the d_drained
+                                  // hand-shake d_full[0] would see two completions -- the direction layer and the next
+                                  // layer 1 -- that no consumer observation separates)
   uint32_t tmem_base;
 };
 
@@ -533,6 +571,24 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   const long long n_groups = gridDim.x / kCg, group = blockIdx.x / kCg;
   const long long n_slots = ((ntiles + kCg - 1) / kCg + n_groups - 1) / n_groups;
   const int n_layers_epi = 8;   // trunk layers with a TMEM->TMEM epilogue (the bottleneck is folded away)
+  // Deferred direction-layer epilogue (round 2).  The 128 softplus + rgb head of a tile are MUFU-bound (~2.8k cycles
+  // for the 16 epilogue warps) and used to run between the direction layer and the NEXT tile's layer-1 epilogue, so the
+  // tensor pipe idled ~3k cycles at every slot boundary (profiles/r02_trace_bf16_encoder_warps.txt: chunk 2 waits 2.9k).
+  // Now the pre-activations are set aside at the boundary and the math runs in kDirPieces pieces inside the next slot,
+  // each in the window after a layer's second epilogue half where these warps wait for the next accumulator anyway:
+  //   single-product mode: the direction layer accumulates into TMEM columns [384,512) -- the A-lo region that mode never
+  //     uses -- and stays there; a piece reads 8 columns with tcgen05.ld (no drain, no d_drained hand-shake);
+  //   split modes (TMEM exactly full): drained at the boundary as before, parked in the thread's local memory (128 B).
+  // The legacy fp32-storage training forward (kTrain == 1) keeps the in-place epilogue.
+  constexpr bool kDefer = kTrain != 1;
+  constexpr bool kDirTmem = kDefer && !kSplit;
+  constexpr int kDirPieces = kDefer ? (kSplit ? 2 : 4) : 1;
+  // Rotated slot boundary (single-product mode): with the direction layer on its own accumulator nothing stops the NEXT
+  // tile's layer 1 (A operand = the encoding in smem, 512 tensor cycles) from being issued BEFORE this tile's direction
+  // layer -- it then runs while the epilogue warps finish layer 8, and its own epilogue overlaps the direction-layer
+  // MMAs (its stores into the A operand wait for them: a_free is committed behind the last direction chunk).  Order of
+  // a slot: [L1 (first slot only)] L2..L8 | L1' of the next tile | direction layer.
+  const bool rot = kDirTmem && SNB_ROTATE && !p.sigma_only;
   const int n_chunks = p.sigma_only ? tab.n_sigma_only : tab.n_total;
 
   // ---------------- one-time setup
@@ -549,6 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     mbar_init(&s.enc_free, 1);
     mbar_init(&s.dir_free, 1);
     mbar_init(&s.rgb_done, kEpiWarps);
+    mbar_init(&s.d_full_dir, 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { if (kCg == 2) tmem_alloc_pair(&s.tmem_base); else tmem_alloc<512>(&s.tmem_base); }
@@ -611,7 +668,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     if (elect_one()) {
       uint32_t it = 0;
       for (long long slot = 0; slot < n_slots; ++slot) {
-        for (int ci = 0; ci < n_chunks; ++ci, ++it) {
+        // rotated order: the next tile's two layer-1 chunks sit between layer 8 and the direction layer
+        const int first = (rot && slot > 0) ? 2 : 0;
+        const int extra = (rot && slot + 1 < n_slots) ? 2 : 0;
+        for (int pos = first; pos < n_chunks + extra; ++pos, ++it) {
+          const int ci = !extra ? pos : (pos < tab.n_sigma_only ? pos : (pos < tab.n_sigma_only + 2 ? pos - tab.n_sigma_only : pos - 2));
           const uint32_t st = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(&s.empty[st], ph ^ 1);
           const Chunk c = tab.c[ci];
@@ -664,15 +725,22 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       for (long long slot = 0; slot < n_slots; ++slot) {
         const uint32_t slot_par = (uint32_t)slot & 1;    // enc_ready / dir_ready / d_drained complete once per slot
         const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3;
-        static_for<T.n_total>([&](auto tag) {
+        // `next`: the chunk belongs to the NEXT slot's layer 1, issued ahead of this slot's direction layer (rot)
+        auto issue_chunk = [&](auto tag, const bool next) {
           constexpr int CI = decltype(tag)::value;
           constexpr Chunk c = T.c[CI];
-          if (CI >= T.n_sigma_only && p.sigma_only) return;
           trace(tr, CI * 4 + 0);
+          if (next) {
+            // the accumulator half this chunk overwrites was drained by layer 8's epilogue of the current tile: the
+            // last (8th, parity 1) completion of the two column quarters of that half
+            static_assert(CI >= 2 || (prior_waits(T, T.n_sigma_only, WAIT_A0, 0) & 1) == 1, "parity of layer 8's a_ready");
+            mbar_wait(&s.a_ready[2 * c.half], 1);
+            mbar_wait(&s.a_ready[2 * c.half + 1], 1);
+          }
           // a_ready[q] completes 8 times per slot (static_assert below): the parity of each wait is static
           auto wait_code = [&](auto code_tag, auto stage_tag) {
             constexpr int w = decltype(code_tag)::value;
-            if (w == WAIT_ENC) mbar_wait(&s.enc_ready, slot_par);
+            if (w == WAIT_ENC) mbar_wait(&s.enc_ready, slot_par ^ (next ? 1u : 0u));
             else if (w == WAIT_DIR) mbar_wait(&s.dir_ready, slot_par);
             else if (w >= WAIT_A0) mbar_wait(&s.a_ready[w - WAIT_A0], prior_waits(T, CI, w, decltype(stage_tag)::value) & 1);
           };
@@ -682,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           mbar_wait(&s.full[st], ph_full);
           tc_fence_after();
           trace(tr, CI * 4 + 2);
-          const uint32_t d = tbase + kColD + (c.layer == 9 ? 0 : c.half * kNh);
+          const uint32_t d = tbase + (c.layer == 9 ? (kDirTmem ? kColAlo : kColD) : kColD + c.half * kNh);
           const uint32_t bh = b_ring0 + st * (kStageBytes >> 4);           // W_hi block
           const uint32_t bl = bh + ((G::kStepBytes * c.steps) >> 4);        // W_lo block
           // K16 steps [kLo, kHi) of this chunk
@@ -741,21 +809,36 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           }
           commit(&s.empty[st]);        // ring slot free (in both CTAs of a pair) once these MMAs retire
           trace(tr, 512 + CI * 4 + 2);
-          if (c.commit & COMMIT_AFREE) commit(&s.a_free);
-          if (c.commit & COMMIT_D0) commit(&s.d_full[0]);
+          // layer 1 issued ahead of the direction layer: its epilogue's stores into the A operand must wait for the
+          // direction layer's MMAs, so that a_free is committed behind the last direction chunk instead
+          if ((c.commit & COMMIT_AFREE) && !next) commit(&s.a_free);
+          if (c.src == SRC_DIR && rot && slot + 1 < n_slots) commit(&s.a_free);
+          if (c.commit & COMMIT_D0) commit((c.layer == 9 && kDirTmem) ? &s.d_full_dir : &s.d_full[0]);
           if (c.commit & COMMIT_D1) commit(&s.d_full[1]);
           if (c.src == SRC_ENC && c.layer == 4 && c.half == 1) commit(&s.enc_free);   // last reader of enc in this slot
           if (c.src == SRC_DIR) commit(&s.dir_free);
           trace(tr, 512 + CI * 4 + 3);
           if (++st == kStages) { st = 0; ph_full ^= 1; }
           trace(tr, CI * 4 + 3);
+        };
+        static_for<T.n_total>([&](auto tag) {
+          constexpr int CI = decltype(tag)::value;
+          if (CI >= T.n_sigma_only && p.sigma_only) return;
+          if (CI < 2 && rot && slot > 0) return;          // issued at the end of the previous slot
+          if (CI == T.n_sigma_only && rot && slot + 1 < n_slots) {
+            issue_chunk(std::integral_constant<int, 0>{}, true);
+            issue_chunk(std::integral_constant<int, 1>{}, true);
+          }
+          issue_chunk(tag, false);
         });
         if (p.sigma_only) {
           // layer 8's epilogue arrives on a_ready[0..3] with nobody waiting: consume the phases
 #pragma unroll
           for (int q = 0; q < 4; ++q) mbar_wait(&s.a_ready[q], prior_waits(T, T.n_sigma_only, WAIT_A0 + q, 0) & 1);
-        } else {
+        } else if (!kDirTmem) {
           // the next slot's layer 1 overwrites D[0,128): wait until the dir-layer epilogue has read it
+          // (kDirTmem: the direction layer has its own accumulator; its next overwrite is ordered behind the
+          // a_ready waits of the next slot's layer 8, which every epilogue thread signals after its last piece)
           mbar_wait(&s.d_drained, slot_par);
         }
       }
@@ -852,7 +935,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       encode_rows(slot + 1, true);
       if (!p.sigma_only) {
         mbar_wait(&s.dir_free, (uint32_t)slot & 1);
-        mbar_wait(&s.rgb_done, (uint32_t)slot & 1);
+        if (kSplit) mbar_wait(&s.rgb_done, (uint32_t)slot & 1);    // the rgb partial sums alias dir[0] there
         encode_rows(slot + 1, false);
       }
     }
@@ -878,12 +961,99 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       }
     };
 
+    // ---------------- direction-layer epilogue (shifted softplus / ReLU, rgb head), in pieces
+    constexpr int kJ4 = 8 / kDirPieces;          // groups of four columns per piece (this thread owns 32 columns)
+    float4 park[(kDefer && kSplit) ? 8 : 1];     // split modes: the drained pre-activations, in local memory
+    const int cdir0 = ch * 32;
+    // rgb partial sums go through the dir-embedding buffer: its last readers (the dir-layer MMAs of the tile the sums
+    // belong to) have retired, and the encoder warps write the next dir embedding only after rgb_done
+    float* rgbp = kSplit ? reinterpret_cast<float*>(s.dir[0]) : s.rgbp_own;     // [4][3][kTile]
+    // piece `pc` of the tile whose row of this thread is point `dpt`; `vreg` = the 32 drained values (kDefer == false)
+    auto dir_piece = [&](int pc, long long dpt, const uint32_t* vreg) {
+      const int col0 = cdir0 + pc * (4 * kJ4);
+      const float4* b4 = reinterpret_cast<const float4*>(s.cst + CL.b[9] + col0);
+      const float4* w0 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + col0);
+      const float4* w1 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + kHalf + col0);
+      const float4* w2 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + 2 * kHalf + col0);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      if (pc > 0) { a0 = rgbp[(ch * 3 + 0) * kTile + row]; a1 = rgbp[(ch * 3 + 1) * kTile + row]; a2 = rgbp[(ch * 3 + 2) * kTile + row]; }
+      uint32_t t8[kDirTmem ? 8 : 1];
+      if constexpr (kDirTmem) {
+        static_assert(!kDirTmem || kJ4 == 2, "a piece is one 8-column tcgen05.ld");
+        tmem_ld8(tbase + lane_base + kColAlo + col0, t8);
+        tmem_wait_ld();
+      }
+      uint32_t g16[kTrain == 2 ? 2 * kJ4 : 1];   // this piece's direction-layer outputs as fp16 pairs
+      float4 keep[4];
+      const float sh = new_activation ? 1.0f : 0.0f;   // shifted softplus: fold the -1 into the bias
+#pragma unroll
+      for (int jj = 0; jj < kJ4; ++jj) {
+        const float4 bb = b4[jj], r0 = w0[jj], r1 = w1[jj], r2 = w2[jj];
+        float x[4];
+        if constexpr (kDirTmem) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(t8[4 * jj + e]);
+        } else if constexpr (kDefer) {
+          const float4 q = park[pc * kJ4 + jj];
+          x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(vreg[4 * jj + e]);
+        }
+        x[0] += bb.x - sh; x[1] += bb.y - sh; x[2] += bb.z - sh; x[3] += bb.w - sh;
+        if (new_activation) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = SNB_SOFTPLUS_POLY ? softplus_poly<!kSplit>(x[e]) : softplus_fast(x[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+        }
+        if (kTrain == 1) {
+          keep[jj & 3] = make_float4(x[0], x[1], x[2], x[3]);
+          if ((jj & 3) == 3) store_block16(keep, p.save_g + (dpt - lane) * kHalf + cdir0 + (jj >> 2) * 16, kHalf, dpt - lane);
+        }
+        if (kTrain == 2) { g16[2 * jj] = pack_half2_sat(x[0], x[1]); g16[2 * jj + 1] = pack_half2_sat(x[2], x[3]); }
+        a0 = fmaf(x[0], r0.x, a0); a0 = fmaf(x[1], r0.y, a0); a0 = fmaf(x[2], r0.z, a0); a0 = fmaf(x[3], r0.w, a0);
+        a1 = fmaf(x[0], r1.x, a1); a1 = fmaf(x[1], r1.y, a1); a1 = fmaf(x[2], r1.z, a1); a1 = fmaf(x[3], r1.w, a1);
+        a2 = fmaf(x[0], r2.x, a2); a2 = fmaf(x[1], r2.y, a2); a2 = fmaf(x[2], r2.z, a2); a2 = fmaf(x[3], r2.w, a2);
+      }
+      if (kTrain == 2 && dpt < p.ppad) {
+        const bool live = dpt < p.n_points;
+#pragma unroll
+        for (int c = 0; c < kJ4 / 2; ++c)
+          *reinterpret_cast<uint4*>(p.a_g + a16_cell(dpt, (col0 >> 3) + c, kHalf)) =
+              live ? make_uint4(g16[4 * c], g16[4 * c + 1], g16[4 * c + 2], g16[4 * c + 3]) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      rgbp[(ch * 3 + 0) * kTile + row] = a0; rgbp[(ch * 3 + 1) * kTile + row] = a1; rgbp[(ch * 3 + 2) * kTile + row] = a2;
+    };
+    // rgb head (nerf.py:144) + the tile's [r, g, b, sigma] rows
+    auto dir_finish = [&](long long dpt) {
+      epi_bar_sync();
+      if (ch == 0 && dpt < p.n_points) {
+        float c[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float x = ((rgbp[k * kTile + row] + rgbp[(3 + k) * kTile + row]) +
+                           (rgbp[(6 + k) * kTile + row] + rgbp[(9 + k) * kTile + row])) + s.cst[CL.rgb_b + k];
+          c[k] = new_activation ? widened_sigmoid_f(x) : sigmoid_f(x);
+        }
+        reinterpret_cast<float4*>(p.out)[dpt] = make_float4(c[0], c[1], c[2], s.sigp[0][row]);
+      }
+      epi_bar_sync();
+      if (lane == 0) mbar_arrive(&s.rgb_done);
+    };
+    bool pending = false;      // the previous slot's direction-layer epilogue is still owed (kDefer)
 
     for (long long slot = 0; slot < n_slots; ++slot) {
-      const long long pt = tile_of(slot) * kTile + row;
+      const long long pt_slot = tile_of(slot) * kTile + row;
       float sig_part = 0.f;
-      // ---------------- trunk + bottleneck epilogues: D (TMEM) -> act -> A (TMEM)
-      for (int l = 0; l < n_layers_epi; ++l) {
+      // ---------------- trunk epilogues: D (TMEM) -> act -> A (TMEM)
+      // rotated order: layer 1's epilogue of this tile ran at the end of the previous slot (li = 8 there)
+      const bool has_next = rot && slot + 1 < n_slots;
+      const int poff = rot ? 1 : 0;         // first layer of the slot after which a deferred piece runs
+      for (int li = (rot && slot > 0) ? 1 : 0; li < n_layers_epi + (has_next ? 1 : 0); ++li) {
+        const int l = li < n_layers_epi ? li : 0;
+        const long long pt = li < n_layers_epi ? pt_slot : tile_of(slot + 1) * kTile + row;
         const float* bias = s.cst + CL.b[l];
         const bool relu = true;
 #pragma unroll 1
@@ -981,7 +1151,21 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           }
         }
         // ---- background work in the idle window before this layer's next accumulator half is ready
-        if (l == 7) {
+        if (kDefer && pending && li >= poff && li < poff + kDirPieces) {
+          // the previous tile's direction-layer epilogue, one piece per layer; sigp[0] still holds that tile's sigma
+          // (rewritten at l == 7 of this slot)
+          const bool trp = (p.debug & 8) && blockIdx.x == 0 && slot == 4 && tid == 0;
+          const long long dpt = tile_of(slot - 1) * kTile + row;
+          if (li == poff) trace(trp, 1024 + 18 * 8 + 5);
+          dir_piece(li - poff, dpt, nullptr);
+          if (li - poff == kDirPieces - 1) {
+            trace(trp, 1024 + 18 * 8 + 3);
+            dir_finish(dpt);
+            pending = false;
+            trace(trp, 1024 + 18 * 8 + 4);
+          }
+        }
+        if (li == 7) {
           // sigma head (nerf.py:136): combine the two column halves of each row
           s.sigp[ch][row] = sig_part;
           epi_bar_sync();
@@ -995,81 +1179,45 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       }
       if (p.sigma_only) continue;
 
-      // ---------------- direction layer epilogue + rgb head + output
+      // ---------------- direction layer: accumulator full -> (drain) -> epilogue now or in the next slot
       {
         const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3 && tid == 0;
         const int tb = 1024 + 18 * 8;
         trace(tr, tb + 0);
-        mbar_wait(&s.d_full[0], ph_d & 1); ph_d ^= 1u;
+        if (kDirTmem) { mbar_wait(&s.d_full_dir, (uint32_t)slot & 1); }
+        else { mbar_wait(&s.d_full[0], ph_d & 1); ph_d ^= 1u; }
         tc_fence_after();
         trace(tr, tb + 1);
-        const float* bias = s.cst + CL.b[9];
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        uint32_t v[32];
-        const int c0 = ch * 32;
-        tmem_ld32(tbase + lane_base + kColD + c0, v);
-        tmem_wait_ld();
-        tc_fence_before();
-        signal(&s.d_drained);      // D[0,128) is in registers: the next slot's layer 1 may overwrite it
-        trace(tr, tb + 2);
-        uint32_t g16[kTrain == 2 ? 16 : 1];        // this thread's 32 direction-layer outputs as fp16 pairs
-        {
-          const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
-          const float4* w0 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + c0);
-          const float4* w1 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + kHalf + c0);
-          const float4* w2 = reinterpret_cast<const float4*>(s.cst + CL.rgb_w + 2 * kHalf + c0);
-          float4 keep[4];
+        if (kDirTmem) {
+          pending = true;            // the accumulator is columns [384,512): nothing to drain
+        } else {
+          uint32_t v[32];
+          tmem_ld32(tbase + lane_base + kColD + cdir0, v);
+          tmem_wait_ld();
+          tc_fence_before();
+          signal(&s.d_drained);      // D[0,128) is in registers: the next slot's layer 1 may overwrite it
+          if constexpr (kDefer) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = b4[j4], r0 = w0[j4], r1 = w1[j4], r2 = w2[j4];
-            // shifted softplus: fold the -1 into the bias
-            const float sh = new_activation ? 1.0f : 0.0f;
-            float x[4] = {__uint_as_float(v[4 * j4]) + (bb.x - sh), __uint_as_float(v[4 * j4 + 1]) + (bb.y - sh),
-                          __uint_as_float(v[4 * j4 + 2]) + (bb.z - sh), __uint_as_float(v[4 * j4 + 3]) + (bb.w - sh)};
-            if (new_activation) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] = softplus_fast(x[e]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
-            }
-            if (kTrain == 1) {
-              keep[j4 & 3] = make_float4(x[0], x[1], x[2], x[3]);
-              if ((j4 & 3) == 3) store_block16(keep, p.save_g + (pt - lane) * kHalf + c0 + (j4 >> 2) * 16, kHalf, pt - lane);
-            }
-            if (kTrain == 2) { g16[2 * j4] = pack_half2_sat(x[0], x[1]); g16[2 * j4 + 1] = pack_half2_sat(x[2], x[3]); }
-            a0 = fmaf(x[0], r0.x, a0); a0 = fmaf(x[1], r0.y, a0); a0 = fmaf(x[2], r0.z, a0); a0 = fmaf(x[3], r0.w, a0);
-            a1 = fmaf(x[0], r1.x, a1); a1 = fmaf(x[1], r1.y, a1); a1 = fmaf(x[2], r1.z, a1); a1 = fmaf(x[3], r1.w, a1);
-            a2 = fmaf(x[0], r2.x, a2); a2 = fmaf(x[1], r2.y, a2); a2 = fmaf(x[2], r2.z, a2); a2 = fmaf(x[3], r2.w, a2);
+            for (int j = 0; j < 8; ++j)
+              park[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                    __uint_as_float(v[4 * j + 3]));
+            pending = true;
+          } else {
+            trace(tr, tb + 2);
+            dir_piece(0, pt_slot, v);
+            trace(tr, tb + 3);
+            dir_finish(pt_slot);
+            trace(tr, tb + 4);
           }
         }
-        if (kTrain == 2 && pt < p.ppad) {
-          const bool live = pt < p.n_points;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(p.a_g + a16_cell(pt, (c0 >> 3) + c, kHalf)) =
-                live ? make_uint4(g16[4 * c], g16[4 * c + 1], g16[4 * c + 2], g16[4 * c + 3]) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        trace(tr, tb + 3);
-        // rgb partial sums go through the dir-embedding buffer: its last readers (this slot's dir-layer MMAs) have
-        // retired, and the encoder warps write the next slot's dir embedding only after rgb_done below
-        float* rgbp = reinterpret_cast<float*>(s.dir[0]);     // [4][3][kTile]
-        rgbp[(ch * 3 + 0) * kTile + row] = a0; rgbp[(ch * 3 + 1) * kTile + row] = a1; rgbp[(ch * 3 + 2) * kTile + row] = a2;
-        epi_bar_sync();
-        if (ch == 0 && pt < p.n_points) {
-          float c[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float x = ((rgbp[k * kTile + row] + rgbp[(3 + k) * kTile + row]) +
-                             (rgbp[(6 + k) * kTile + row] + rgbp[(9 + k) * kTile + row])) + s.cst[CL.rgb_b + k];
-            c[k] = new_activation ? widened_sigmoid_f(x) : sigmoid_f(x);
-          }
-          reinterpret_cast<float4*>(p.out)[pt] = make_float4(c[0], c[1], c[2], s.sigp[0][row]);
-        }
-        epi_bar_sync();
-        if (lane == 0) mbar_arrive(&s.rgb_done);
-        trace(tr, tb + 4);
+        if (kDefer) trace(tr, tb + 2);
       }
+    }
+    if (kDefer && pending) {       // the last slot's direction-layer epilogue
+      const long long dpt = tile_of(n_slots - 1) * kTile + row;
+#pragma unroll 1
+      for (int pc = 0; pc < kDirPieces; ++pc) dir_piece(pc, dpt, nullptr);
+      dir_finish(dpt);
     }
   }
   tc_fence_before();

@@ -417,6 +417,250 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
 }
 
 // ---------------------------------------------------------------------------------------
+// Four-samples-per-thread compositing (round 2): the fast path for S % 4 == 0, S <= 128 (the 64 / 128-sample passes
+// of every BASELINE config).  The warp-per-ray kernels above issue ~5.5 instructions per sample and lane (353 warp
+// instructions per 64-sample ray, ncu) and are issue-bound at ~2.7 TB/s; here a thread owns FOUR consecutive samples
+// -- one 16-byte load each of z / noise / g_w, four of raw, one 16-byte store of the weights (four of g_raw) --
+// multiplies its four (1 - alpha) factors serially, and only the per-thread products go through the shuffle scan.
+// The S/4 threads of a ray form an aligned group of L = 8, 16 or 32 lanes, 32 / L rays per warp pass, so the scan has
+// log2(L) steps per four samples instead of five per sample, and 32 / L times the bytes are in flight per warp.
+// Element-wise arithmetic (separately rounded delta, alpha, the 1e-10) is the warp-per-ray kernels'.
+// ---------------------------------------------------------------------------------------
+struct Quad {                 // what a thread derives for its four samples
+  float alpha[4], T[4], e[4], delta[4], sg[4];
+};
+template <int L>
+__device__ __forceinline__ void composite_quad(const float4 zq, const float znext, const bool last, const float dnorm,
+                                               const float4 sig, const bool has_noise, const float4 nz,
+                                               const float noise_std, const bool act, const int sl, Quad& q) {
+  const float zz[5] = {zq.x, zq.y, zq.z, zq.w, znext};
+  const float ss[4] = {sig.x, sig.y, sig.z, sig.w};
+  const float nn[4] = {nz.x, nz.y, nz.z, nz.w};
+  float t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float d = (k == 3 && last) ? 1e10f : __fsub_rn(zz[k + 1], zz[k]);
+    d = __fmul_rn(d, dnorm);
+    float sg = ss[k];
+    if (has_noise) sg = __fadd_rn(sg, __fmul_rn(nn[k], noise_std));
+    const float e = act ? expf(-__fmul_rn(d, fmaxf(sg, 0.f))) : 1.0f;
+    const float a = act ? __fsub_rn(1.0f, e) : 0.f;
+    q.delta[k] = d; q.sg[k] = sg; q.e[k] = e; q.alpha[k] = a;
+    t[k] = act ? __fadd_rn(__fsub_rn(1.0f, a), 1e-10f) : 1.0f;
+  }
+  const float p0 = t[0], p1 = p0 * t[1], p2 = p1 * t[2], p3 = p2 * t[3];
+  float scan = p3;            // inclusive product scan of the per-thread products over the ray's lane group
+#pragma unroll
+  for (int off = 1; off < L; off <<= 1) {
+    const float up = __shfl_up_sync(kFull, scan, off, L);
+    if (sl >= off) scan *= up;
+  }
+  float excl = __shfl_up_sync(kFull, scan, 1, L);
+  if (sl == 0) excl = 1.0f;
+  q.T[0] = excl; q.T[1] = excl * p0; q.T[2] = excl * p1; q.T[3] = excl * p2;
+}
+
+template <int L>
+__global__ void __launch_bounds__(256) composite_fwd4_kernel(
+    const float* __restrict__ raw, int raw_channels, const float* __restrict__ z_vals,
+    const float* __restrict__ rays, const float* __restrict__ noise, float noise_std, int white_back,
+    long long n_rays, int S, float* __restrict__ rgb_out, float* __restrict__ depth_out,
+    float* __restrict__ w_out, LossSpec ls, float* __restrict__ loss_out, float* __restrict__ loss_ws) {
+  constexpr int kRpw = 32 / L;
+  const int lane = threadIdx.x & 31, sl = lane & (L - 1), sub = lane / L;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long ngroups = (n_rays + kRpw - 1) / kRpw;
+  const int nq = S >> 2;
+  const bool last = sl == nq - 1;
+  float loss_rgb = 0.f, loss_depth = 0.f;      // lanes with sl == 0: their rays' share of the two loss sums
+  for (long long g = warp; g < ngroups; g += nwarps) {
+    const long long ray = g * kRpw + sub;
+    const bool act = ray < n_rays && sl < nq;
+    float4 zq = make_float4(0.f, 0.f, 0.f, 0.f), sig = zq, nz = zq, c[4] = {zq, zq, zq, zq};
+    float dnorm = 0.f;
+    if (act) {
+      const long long p0 = ray * S + 4 * sl;
+      zq = *reinterpret_cast<const float4*>(z_vals + p0);
+      if (raw_channels == 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = reinterpret_cast<const float4*>(raw)[p0 + k];
+        sig = make_float4(c[0].w, c[1].w, c[2].w, c[3].w);
+      } else {
+        sig = *reinterpret_cast<const float4*>(raw + p0);
+      }
+      if (noise != nullptr) nz = *reinterpret_cast<const float4*>(noise + p0);
+      const float dx = rays[ray * 8 + 3], dy = rays[ray * 8 + 4], dz = rays[ray * 8 + 5];
+      dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+    const float znext = __shfl_down_sync(kFull, zq.x, 1);
+    Quad q;
+    composite_quad<L>(zq, znext, last, dnorm, sig, noise != nullptr, nz, noise_std, act, sl, q);
+    const float zz[4] = {zq.x, zq.y, zq.z, zq.w};
+    float w[4], ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aw = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      w[k] = q.alpha[k] * q.T[k];
+      ar = fmaf(w[k], c[k].x, ar); ag = fmaf(w[k], c[k].y, ag); ab = fmaf(w[k], c[k].z, ab);
+      ad = fmaf(w[k], zz[k], ad);
+      aw += w[k];
+    }
+    if (act) *reinterpret_cast<float4*>(w_out + ray * S + 4 * sl) = make_float4(w[0], w[1], w[2], w[3]);
+    if (rgb_out != nullptr || depth_out != nullptr) {
+#pragma unroll
+      for (int off = L / 2; off > 0; off >>= 1) {
+        ar += __shfl_xor_sync(kFull, ar, off);
+        ag += __shfl_xor_sync(kFull, ag, off);
+        ab += __shfl_xor_sync(kFull, ab, off);
+        ad += __shfl_xor_sync(kFull, ad, off);
+        aw += __shfl_xor_sync(kFull, aw, off);
+      }
+      if (sl == 0 && ray < n_rays) {
+        if (rgb_out != nullptr) {
+          if (white_back) {  // rgb + 1 - weights_sum  (rendering.py:245-246)
+            ar = __fsub_rn(__fadd_rn(ar, 1.0f), aw);
+            ag = __fsub_rn(__fadd_rn(ag, 1.0f), aw);
+            ab = __fsub_rn(__fadd_rn(ab, 1.0f), aw);
+          }
+          rgb_out[ray * 3 + 0] = ar; rgb_out[ray * 3 + 1] = ag; rgb_out[ray * 3 + 2] = ab;
+          if (ls.trgb != nullptr) {
+            const float e0 = ar - ls.trgb[ray * 3], e1 = ag - ls.trgb[ray * 3 + 1], e2 = ab - ls.trgb[ray * 3 + 2];
+            loss_rgb = fmaf(ls.wr != nullptr ? ls.wr[ray] : ls.wr0, e0 * e0 + e1 * e1 + e2 * e2, loss_rgb);
+          }
+        }
+        if (depth_out != nullptr) {
+          depth_out[ray] = ad;
+          if (ls.tdepth != nullptr)
+            loss_depth = fmaf(ls.wd != nullptr ? ls.wd[ray] : ls.wd0, smooth_l1(ad - ls.tdepth[ray]), loss_depth);
+        }
+      }
+    }
+  }
+  if (loss_out != nullptr) {
+    // same two-level fixed-order reduction as composite_fwd_kernel; the warp's share first (lanes with sl != 0 hold 0)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      loss_rgb += __shfl_xor_sync(kFull, loss_rgb, off);
+      loss_depth += __shfl_xor_sync(kFull, loss_depth, off);
+    }
+    __shared__ float part[8][2];
+    __shared__ bool last_block;
+    if (lane == 0) { part[threadIdx.x >> 5][0] = loss_rgb; part[threadIdx.x >> 5][1] = loss_depth; }
+    __syncthreads();
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(loss_ws);
+    float* partials = loss_ws + 4;
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int i = 0; i < 8; ++i) { a += part[i][0]; b += part[i][1]; }
+      partials[2 * blockIdx.x] = a; partials[2 * blockIdx.x + 1] = b;
+      __threadfence();
+      last_block = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_block && threadIdx.x < 32) {
+      __threadfence();
+      float a = 0.f, b = 0.f;
+      for (unsigned int i = lane; i < gridDim.x; i += 32) {
+        a += __ldcg(partials + 2 * i); b += __ldcg(partials + 2 * i + 1);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(kFull, a, off); b += __shfl_xor_sync(kFull, b, off); }
+      if (lane == 0) { loss_out[0] = a; loss_out[1] = b; *ticket = 0u; }
+    }
+  }
+}
+
+// Backward in the same mapping: everything of a thread's four samples stays in registers (the warp-per-ray kernel
+// parks alpha / T / gw w in shared memory and reads raw twice), the suffix sums sum_{k>i} gw_k w_k are a serial sum
+// inside the thread plus a log2(L)-step shuffle scan of the per-thread totals.
+template <int L>
+__global__ void __launch_bounds__(256) composite_bwd4_kernel(
+    const float* __restrict__ raw, const float* __restrict__ z_vals, const float* __restrict__ rays,
+    const float* __restrict__ noise, float noise_std, int white_back, const float* __restrict__ g_rgb,
+    const float* __restrict__ g_depth, const float* __restrict__ g_w, long long n_rays, int S,
+    float* __restrict__ g_raw, LossSpec ls, const float* __restrict__ out_rgb, const float* __restrict__ out_depth,
+    const float* __restrict__ g_loss, unsigned int* __restrict__ g_amax) {
+  constexpr int kRpw = 32 / L;
+  const int lane = threadIdx.x & 31, sl = lane & (L - 1), sub = lane / L;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long ngroups = (n_rays + kRpw - 1) / kRpw;
+  const int nq = S >> 2;
+  const bool last = sl == nq - 1;
+  float amax = 0.f;               // max |g_raw| written by this thread (for the 16-bit backward's scaling)
+  for (long long g = warp; g < ngroups; g += nwarps) {
+    const long long ray = g * kRpw + sub;
+    const bool act = ray < n_rays && sl < nq;
+    float4 zq = make_float4(0.f, 0.f, 0.f, 0.f), nz = zq, gwq = zq, c[4] = {zq, zq, zq, zq};
+    float dnorm = 0.f, gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f;
+    const long long p0 = ray * S + 4 * sl;
+    if (act) {
+      zq = *reinterpret_cast<const float4*>(z_vals + p0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c[k] = reinterpret_cast<const float4*>(raw)[p0 + k];
+      if (noise != nullptr) nz = *reinterpret_cast<const float4*>(noise + p0);
+      if (g_w != nullptr) gwq = *reinterpret_cast<const float4*>(g_w + p0);
+      const float dx = rays[ray * 8 + 3], dy = rays[ray * 8 + 4], dz = rays[ray * 8 + 5];
+      dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+      if (g_rgb != nullptr) { gr = g_rgb[ray * 3]; gg = g_rgb[ray * 3 + 1]; gb = g_rgb[ray * 3 + 2]; }
+      if (g_depth != nullptr) gd = g_depth[ray];
+      // fused losses: d loss[0] / d rgb_c = 2 wr (rgb_c - t_c), d loss[1] / d depth = wd smooth_l1'(depth - t)
+      if (ls.trgb != nullptr) {
+        const float k = 2.0f * (ls.wr != nullptr ? ls.wr[ray] : ls.wr0) * (g_loss != nullptr ? g_loss[0] : 1.0f);
+        gr = fmaf(k, out_rgb[ray * 3] - ls.trgb[ray * 3], gr);
+        gg = fmaf(k, out_rgb[ray * 3 + 1] - ls.trgb[ray * 3 + 1], gg);
+        gb = fmaf(k, out_rgb[ray * 3 + 2] - ls.trgb[ray * 3 + 2], gb);
+      }
+      if (ls.tdepth != nullptr) {
+        const float k = (ls.wd != nullptr ? ls.wd[ray] : ls.wd0) * (g_loss != nullptr ? g_loss[1] : 1.0f);
+        gd = fmaf(k, smooth_l1_grad(out_depth[ray] - ls.tdepth[ray]), gd);
+      }
+    }
+    const float gwb = white_back ? (gr + gg + gb) : 0.f;
+    const float znext = __shfl_down_sync(kFull, zq.x, 1);
+    Quad q;
+    composite_quad<L>(zq, znext, last, dnorm, make_float4(c[0].w, c[1].w, c[2].w, c[3].w), noise != nullptr, nz,
+                      noise_std, act, sl, q);
+    const float zz[4] = {zq.x, zq.y, zq.z, zq.w};
+    const float gwv[4] = {gwq.x, gwq.y, gwq.z, gwq.w};
+    float gw[4], v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      gw[k] = gr * c[k].x + gg * c[k].y + gb * c[k].z + gd * zz[k] - gwb;
+      if (g_w != nullptr) gw[k] += gwv[k];
+      v[k] = act ? gw[k] * q.alpha[k] * q.T[k] : 0.f;     // gw_k w_k
+    }
+    // exclusive suffix sums: inside the thread, then over the later threads of the ray
+    const float s2 = v[3], s1 = v[3] + v[2], s0 = s1 + v[1], tot = s0 + v[0];
+    float scan = tot;
+#pragma unroll
+    for (int off = 1; off < L; off <<= 1) {
+      const float dn = __shfl_down_sync(kFull, scan, off, L);
+      if (sl + off < L) scan += dn;
+    }
+    float tail = __shfl_down_sync(kFull, scan, 1, L);
+    if (sl == L - 1) tail = 0.f;
+    const float suf[4] = {tail + s0, tail + s1, tail + s2, tail};
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w = q.alpha[k] * q.T[k];
+        const float galpha = gw[k] * q.T[k] - suf[k] / (__fadd_rn(__fsub_rn(1.0f, q.alpha[k]), 1e-10f));
+        const float gsig = q.sg[k] > 0.f ? galpha * q.delta[k] * q.e[k] : 0.f;
+        reinterpret_cast<float4*>(g_raw)[p0 + k] = make_float4(gr * w, gg * w, gb * w, gsig);
+        amax = fmaxf(fmaxf(amax, fabsf(gsig)), fmaxf(fmaxf(fabsf(gr * w), fabsf(gg * w)), fabsf(gb * w)));
+      }
+    }
+  }
+  if (g_amax != nullptr) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(kFull, amax, off));
+    // non-negative floats order like their bit patterns; NaN / inf gradients saturate the statistic
+    if (lane == 0 && amax > 0.f) atomicMax(g_amax, __float_as_uint(amax == amax ? fminf(amax, 3.0e38f) : 3.0e38f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // inverse-CDF sampling.  One warp per ray; cdf (M+1 floats) and, for the merged variant, the
 // S+Ni depths live in the warp's slice of shared memory.
 //   sample_pdf:       in 4*(M + M+1) B/ray (+4*Ni u), out 4*Ni B/ray
@@ -718,6 +962,13 @@ int launch_embed(const float* x, int64_t n, int C, int L, float* out, cudaStream
   return check_launch("embed_kernel");
 }
 
+// the four-samples-per-thread kernels need rows of whole 16-byte quads: S % 4 == 0 (and at most 32 threads per ray)
+// and 16-byte aligned per-sample tensors; everything else takes the warp-per-ray kernels
+static bool composite_quad_ok(int S, const void* raw, const void* z, const void* a, const void* b) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return S >= 4 && S <= 128 && (S & 3) == 0 && al(raw) && al(z) && al(a) && al(b);
+}
+
 static LossSpec make_loss_spec(const SnbLossSpec* l) {
   LossSpec ls{};
   if (l != nullptr) {
@@ -735,6 +986,18 @@ int launch_composite(const float* raw, int raw_channels, const float* z, const f
                                         ? SNB_OK : fail(SNB_ERR_CUDA, "cudaMemsetAsync(loss)");
     return SNB_OK;
   }
+  static const bool warp_per_ray = getenv("SNB_COMPOSITE_WARP_PER_RAY") != nullptr;   // A/B timing of the two mappings
+  if (composite_quad_ok(S, raw, z, noise, w) && !warp_per_ray) {
+    // four samples per thread: the ray's S/4 threads in a lane group of L = 8 / 16 / 32, 32 / L rays per warp pass
+    const int L = S <= 32 ? 8 : (S <= 64 ? 16 : 32);
+    int grid = grid_for(n_rays, 8 * (32 / L), device_sms() * 8);
+    if (loss_out != nullptr && grid > (SNB_LOSS_WS_FLOATS - 4) / 2) grid = (SNB_LOSS_WS_FLOATS - 4) / 2;
+    const LossSpec ls = make_loss_spec(loss);
+    if (L == 8) composite_fwd4_kernel<8><<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays, S, rgb, depth, w, ls, loss_out, loss_ws);
+    else if (L == 16) composite_fwd4_kernel<16><<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays, S, rgb, depth, w, ls, loss_out, loss_ws);
+    else composite_fwd4_kernel<32><<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays, S, rgb, depth, w, ls, loss_out, loss_ws);
+    return check_launch("composite_fwd4_kernel");
+  }
   int grid = grid_for(n_rays, 8, device_sms() * 8);
   if (loss_out != nullptr && grid > (SNB_LOSS_WS_FLOATS - 4) / 2) grid = (SNB_LOSS_WS_FLOATS - 4) / 2;
   composite_fwd_kernel<<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays,
@@ -747,6 +1010,17 @@ int launch_composite_bwd(const float* raw, const float* z, const float* rays, co
                           int S, float* g_raw, const SnbLossSpec* loss, const float* out_rgb, const float* out_depth,
                           const float* g_loss, float* g_amax, cudaStream_t st) {
   if (n_rays == 0) return SNB_OK;
+  static const bool warp_per_ray = getenv("SNB_COMPOSITE_WARP_PER_RAY") != nullptr;
+  if (composite_quad_ok(S, raw, z, noise, g_w) && (reinterpret_cast<uintptr_t>(g_raw) & 15) == 0 && !warp_per_ray) {
+    const int L = S <= 32 ? 8 : (S <= 64 ? 16 : 32);
+    const int grid = grid_for(n_rays, 8 * (32 / L), device_sms() * 6);
+    const LossSpec ls = make_loss_spec(loss);
+    unsigned int* am = reinterpret_cast<unsigned int*>(g_amax);
+    if (L == 8) composite_bwd4_kernel<8><<<grid, 256, 0, st>>>(raw, z, rays, noise, noise_std, white_back, g_rgb, g_depth, g_w, n_rays, S, g_raw, ls, out_rgb, out_depth, g_loss, am);
+    else if (L == 16) composite_bwd4_kernel<16><<<grid, 256, 0, st>>>(raw, z, rays, noise, noise_std, white_back, g_rgb, g_depth, g_w, n_rays, S, g_raw, ls, out_rgb, out_depth, g_loss, am);
+    else composite_bwd4_kernel<32><<<grid, 256, 0, st>>>(raw, z, rays, noise, noise_std, white_back, g_rgb, g_depth, g_w, n_rays, S, g_raw, ls, out_rgb, out_depth, g_loss, am);
+    return check_launch("composite_bwd4_kernel");
+  }
   const size_t smem = (size_t)8 * 3 * S * sizeof(float);
   if (smem > 96 * 1024) return fail(SNB_ERR_UNSUPPORTED, "snb_composite_backward: too many samples per ray (%d)", S);
   static SmemOptIn optin;

@@ -32,7 +32,7 @@ def make_proj(out, seed):
 def test_composite_backward_matches_autograd():
     from sinnerf_b200.rendering import _Composite
     g = torch.Generator().manual_seed(3)
-    for S in (2, 33, 64, 128):
+    for S in (2, 4, 33, 36, 64, 96, 128, 132):     # both thread mappings of composite_bwd (see test_gpu_parity)
         n = 41
         rays = torch.randn(n, 8, generator=g)
         z = torch.sort(torch.rand(n, S, generator=g) * 4 + 2, -1)[0]

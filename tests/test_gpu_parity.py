@@ -196,7 +196,9 @@ def test_composite_known_answer_and_oracle():
     g = torch.Generator().manual_seed(11)
     # S = 1 is degenerate in the reference itself (deltas[:, :1] of an empty tensor is empty,
     # rendering.py:215-218), so the smallest meaningful S is 2
-    for S in (2, 31, 64, 100, 128):
+    # S % 4 == 0 up to 128 runs the four-samples-per-thread kernels (lane groups of 8 / 16 / 32, partly filled for
+    # S = 36 / 96; 77 rays leave the last warp pass ragged), everything else the warp-per-ray kernel
+    for S in (2, 4, 31, 36, 64, 96, 100, 128, 132):
         n = 77
         rays = torch.randn(n, 8, generator=g)
         z = torch.sort(torch.rand(n, S, generator=g) * 4 + 2, -1)[0]

@@ -20,9 +20,11 @@ ap.add_argument("--rays", type=int, default=160000)
 ap.add_argument("--samples", type=int, default=128)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--sigma-only", action="store_true")
+ap.add_argument("--dump", default="", help="save the output tensor here (A/B comparison of builds)")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
+torch.manual_seed(0)
 lib = _lib.load()
 prec = _lib.precision_id(args.precision)
 m = NeRF(use_new_activation=True)
@@ -56,3 +58,5 @@ flops = 2 * (982528 // 2 if args.sigma_only else 593408) * n * S
 print(f"precision={args.precision} debug={os.environ.get('SNB_TC_DEBUG', '0')} rays={n} S={S} "
       f"ms={ms:.3f} (median {sorted(ts)[len(ts) // 2]:.3f})  {flops / ms / 1e9:.1f} TFLOP/s algorithmic  "
       f"{n * S / 128 / 148 :.0f} tiles/SM  {ms * 1e3 / (n * S / 128 / 148):.2f} us/tile")
+if args.dump:
+    torch.save(raw.cpu(), args.dump)

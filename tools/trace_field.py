@@ -13,7 +13,7 @@ buf = (C.c_longlong * 2048)()
 lib.snb_debug_trace.argtypes = [C.POINTER(C.c_longlong), C.c_int]
 assert lib.snb_debug_trace(buf, 2048) == 0
 t = list(buf)
-t0 = t[0]
+t0 = min(t[ci * 4] for ci in range(35) if t[ci * 4] > 0)   # rotated order: chunks 0/1 are issued near the END of the slot
 print("MMA warp: chunk: [loop top] [after A/enc waits] [after full wait] [after issue]   (cycles since slot start)")
 for ci in range(35):
     a, b, c, d = (t[ci * 4 + k] - t0 for k in range(4))
@@ -25,6 +25,7 @@ print("epilogue warp 0: (layer, half): [start waiting d_full] [observed] [ld don
 for lh in range(16):
     e = [t[1024 + lh * 8 + k] - t0 for k in range(5)]
     print(f"  l={lh // 2} h={lh % 2}: wait_from {e[0]:7d}  d_full {e[1]:7d}  ld {e[2] - e[1]:5d}  q0 +{e[3] - e[1]:5d}  q1 +{e[4] - e[1]:5d}")
-e = [t[1024 + 18 * 8 + k] - t0 for k in range(5)]
+e = [t[1024 + 18 * 8 + k] - t0 for k in range(6)]
 print(f"  dir layer: wait_from {e[0]:7d}  d_full {e[1]:7d}  drained +{e[2] - e[1]:5d}  math +{e[3] - e[1]:5d}  head/out +{e[4] - e[1]:5d}")
-print(f"  slot length (MMA warp, chunk 0 top -> chunk 34 issued): {t[34 * 4 + 3] - t0}")
+print(f"  deferred pieces (next slot): first piece starts {e[5] + t0 - t0:7d}" if t[1024 + 18 * 8 + 5] > 0 else "  (direction-layer epilogue not deferred)")
+print(f"  slot length (MMA warp, first chunk top -> chunk 34 issued): {t[34 * 4 + 3] - t0}")
