@@ -328,38 +328,6 @@ __device__ __forceinline__ float softplus_fast(float s) {
   return fmaf(__log2f(1.0f + t), 0.6931471805599453f, fmaxf(s, 0.0f));   // max(s,0) + log1p(t)  (lg2.approx)
 }
 
-// One-MUFU variant: log1p(t) on (0, 1] as t * q(t), q a minimax polynomial (degree 7: max abs error 2.5e-7 evaluated
-// in fp32 -- the rounding level of the O(1) result; degree 4 for the single-product mode: 4e-5, three orders below the
-// bf16 rounding of that mode's operands).  The direction-layer epilogue is 128 softplus per point and was MUFU-bound
-// (2 MUFU each, 16 lanes/clk/SM = 2048 cycles per tile); the FMA pipe has the room (8 resp. 5 FMAs).
-template <bool kLowPrec>
-__device__ __forceinline__ float softplus_poly(float s) {
-  float t;                                                             // exp(-|s|) in (0, 1]
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * fabsf(s)));
-  float q;
-  if (kLowPrec) {
-    q = fmaf(0.04155111312866211f, t, -0.157838374376297f);
-    q = fmaf(q, t, 0.30656111240386963f);
-    q = fmaf(q, t, -0.4970308542251587f);
-    q = fmaf(q, t, 0.9999449849128723f);
-  } else {
-    q = fmaf(-0.008574675768613815f, t, 0.044214192777872086f);
-    q = fmaf(q, t, -0.10785368084907532f);
-    q = fmaf(q, t, 0.17757023870944977f);
-    q = fmaf(q, t, -0.2449961155653f);
-    q = fmaf(q, t, 0.3327617645263672f);
-    q = fmaf(q, t, -0.49997448921203613f);
-    q = fmaf(q, t, 0.9999998211860657f);
-  }
-  return fmaf(q, t, fmaxf(s, 0.0f));
-}
-#ifndef SNB_ROTATE
-#define SNB_ROTATE 0
-#endif
-#ifndef SNB_SOFTPLUS_POLY
-#define SNB_SOFTPLUS_POLY 0
-#endif
-
 // sin / cos for the positional encoding of the single-product bf16 mode: two-constant Cody-Waite reduction to
 // [-pi, pi] and the MUFU approximations (abs error ~1e-6 for |x| up to ~1e4 -- three orders below bf16's 2^-9
 // rounding of the encoded value), ~8 instructions instead of sincosf's ~50.  In that mode an MMA phase is only 512
@@ -571,25 +539,20 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
   const long long n_groups = gridDim.x / kCg, group = blockIdx.x / kCg;
   const long long n_slots = ((ntiles + kCg - 1) / kCg + n_groups - 1) / n_groups;
   const int n_layers_epi = 8;   // trunk layers with a TMEM->TMEM epilogue (the bottleneck is folded away)
-  // Deferred direction-layer epilogue (round 2).  The 128 softplus + rgb head of a tile are MUFU-bound (~2.8k cycles
-  // for the 16 epilogue warps) and used to run between the direction layer and the NEXT tile's layer-1 epilogue, so the
-  // tensor pipe idled ~3k cycles at every slot boundary (profiles/r02_trace_bf16_encoder_warps.txt: chunk 2 waits 2.9k).
-  // Now the pre-activations are set aside at the boundary and the math runs in kDirPieces pieces inside the next slot,
-  // each in the window after a layer's second epilogue half where these warps wait for the next accumulator anyway:
-  //   single-product mode: the direction layer accumulates into TMEM columns [384,512) -- the A-lo region that mode never
-  //     uses -- and stays there; a piece reads 8 columns with tcgen05.ld (no drain, no d_drained hand-shake);
-  //   split modes (TMEM exactly full): drained at the boundary as before, parked in the thread's local memory (128 B).
-  // The legacy fp32-storage training forward (kTrain == 1) keeps the in-place epilogue.
-  constexpr bool kDefer = kTrain != 1;
-  constexpr bool kDirTmem = kDefer && !kSplit;
-  constexpr int kDirPieces = kDefer ? (kSplit ? 2 : 4) : 1;
-  // Rotated slot boundary (single-product mode): with the direction layer on its own accumulator nothing stops the NEXT
-  // tile's layer 1 (A operand = the encoding in smem, 512 tensor cycles) from being issued BEFORE this tile's direction
-  // layer -- it then runs while the epilogue warps finish layer 8, and its own epilogue overlaps the direction-layer
-  // MMAs (its stores into the A operand wait for them: a_free is committed behind the last direction chunk).  Order of
-  // a slot: [L1 (first slot only)] L2..L8 | L1' of the next tile | direction layer.
-  const bool rot = kDirTmem && SNB_ROTATE && !p.sigma_only;
   const int n_chunks = p.sigma_only ? tab.n_sigma_only : tab.n_total;
+  // Deferred direction-layer epilogue (round 2, single-product mode).  The 128 softplus + rgb head of a tile are
+  // MUFU-bound (~2.8k cycles for the 16 epilogue warps) and used to run between the direction layer and the NEXT tile's
+  // layer-1 epilogue: the tensor pipe idled ~2.9k of a 26k-cycle slot at every slot boundary
+  // (profiles/r02b_trace_bf16_before_deferral.txt, chunk 2).  The single-product mode never uses the A-lo columns
+  // [384,512) of TMEM, so there the direction layer accumulates into THEM and the result simply stays: no drain, no
+  // d_drained hand-shake, the next tile's layer 1 starts at once, and the epilogue warps work the pre-activations off in
+  // four 8-column pieces (one tcgen05.ld each) in the windows where they wait for the next accumulator anyway -- after
+  // the second epilogue half of layers 1..4 of the next slot (slot 24.4k cycles, r02b_trace_bf16_deferred_dir_epilogue.txt).
+  // The split modes keep the in-place epilogue: TMEM is exactly full there, and a variant that parked the drained values
+  // in local memory shortened the slot by 4 % in cycles and not at all in time -- that kernel runs at the 1 kW power cap
+  // and the clock gave the cycles back (profiles/r02b_field_variants_ab.txt, r02b_trace_f16x3_deferred_experiment.txt).
+  constexpr bool kDirTmem = !kSplit && kTrain != 1;      // (the legacy fp32-storage training forward keeps the old order)
+  constexpr int kDirPieces = kDirTmem ? 4 : 1;
 
   // ---------------- one-time setup
   for (int i = tid; i < kConstFloats; i += kThreads) s.cst[i] = g_cst[i];
@@ -668,11 +631,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
     if (elect_one()) {
       uint32_t it = 0;
       for (long long slot = 0; slot < n_slots; ++slot) {
-        // rotated order: the next tile's two layer-1 chunks sit between layer 8 and the direction layer
-        const int first = (rot && slot > 0) ? 2 : 0;
-        const int extra = (rot && slot + 1 < n_slots) ? 2 : 0;
-        for (int pos = first; pos < n_chunks + extra; ++pos, ++it) {
-          const int ci = !extra ? pos : (pos < tab.n_sigma_only ? pos : (pos < tab.n_sigma_only + 2 ? pos - tab.n_sigma_only : pos - 2));
+        for (int ci = 0; ci < n_chunks; ++ci, ++it) {
           const uint32_t st = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(&s.empty[st], ph ^ 1);
           const Chunk c = tab.c[ci];
@@ -725,22 +684,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       for (long long slot = 0; slot < n_slots; ++slot) {
         const uint32_t slot_par = (uint32_t)slot & 1;    // enc_ready / dir_ready / d_drained complete once per slot
         const bool tr = (p.debug & 8) && blockIdx.x == 0 && slot == 3;
-        // `next`: the chunk belongs to the NEXT slot's layer 1, issued ahead of this slot's direction layer (rot)
-        auto issue_chunk = [&](auto tag, const bool next) {
+        static_for<T.n_total>([&](auto tag) {
           constexpr int CI = decltype(tag)::value;
           constexpr Chunk c = T.c[CI];
+          if (CI >= T.n_sigma_only && p.sigma_only) return;
           trace(tr, CI * 4 + 0);
-          if (next) {
-            // the accumulator half this chunk overwrites was drained by layer 8's epilogue of the current tile: the
-            // last (8th, parity 1) completion of the two column quarters of that half
-            static_assert(CI >= 2 || (prior_waits(T, T.n_sigma_only, WAIT_A0, 0) & 1) == 1, "parity of layer 8's a_ready");
-            mbar_wait(&s.a_ready[2 * c.half], 1);
-            mbar_wait(&s.a_ready[2 * c.half + 1], 1);
-          }
           // a_ready[q] completes 8 times per slot (static_assert below): the parity of each wait is static
           auto wait_code = [&](auto code_tag, auto stage_tag) {
             constexpr int w = decltype(code_tag)::value;
-            if (w == WAIT_ENC) mbar_wait(&s.enc_ready, slot_par ^ (next ? 1u : 0u));
+            if (w == WAIT_ENC) mbar_wait(&s.enc_ready, slot_par);
             else if (w == WAIT_DIR) mbar_wait(&s.dir_ready, slot_par);
             else if (w >= WAIT_A0) mbar_wait(&s.a_ready[w - WAIT_A0], prior_waits(T, CI, w, decltype(stage_tag)::value) & 1);
           };
@@ -809,10 +761,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           }
           commit(&s.empty[st]);        // ring slot free (in both CTAs of a pair) once these MMAs retire
           trace(tr, 512 + CI * 4 + 2);
-          // layer 1 issued ahead of the direction layer: its epilogue's stores into the A operand must wait for the
-          // direction layer's MMAs, so that a_free is committed behind the last direction chunk instead
-          if ((c.commit & COMMIT_AFREE) && !next) commit(&s.a_free);
-          if (c.src == SRC_DIR && rot && slot + 1 < n_slots) commit(&s.a_free);
+          if (c.commit & COMMIT_AFREE) commit(&s.a_free);
           if (c.commit & COMMIT_D0) commit((c.layer == 9 && kDirTmem) ? &s.d_full_dir : &s.d_full[0]);
           if (c.commit & COMMIT_D1) commit(&s.d_full[1]);
           if (c.src == SRC_ENC && c.layer == 4 && c.half == 1) commit(&s.enc_free);   // last reader of enc in this slot
@@ -820,16 +769,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           trace(tr, 512 + CI * 4 + 3);
           if (++st == kStages) { st = 0; ph_full ^= 1; }
           trace(tr, CI * 4 + 3);
-        };
-        static_for<T.n_total>([&](auto tag) {
-          constexpr int CI = decltype(tag)::value;
-          if (CI >= T.n_sigma_only && p.sigma_only) return;
-          if (CI < 2 && rot && slot > 0) return;          // issued at the end of the previous slot
-          if (CI == T.n_sigma_only && rot && slot + 1 < n_slots) {
-            issue_chunk(std::integral_constant<int, 0>{}, true);
-            issue_chunk(std::integral_constant<int, 1>{}, true);
-          }
-          issue_chunk(tag, false);
         });
         if (p.sigma_only) {
           // layer 8's epilogue arrives on a_ready[0..3] with nobody waiting: consume the phases
@@ -963,12 +902,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
 
     // ---------------- direction-layer epilogue (shifted softplus / ReLU, rgb head), in pieces
     constexpr int kJ4 = 8 / kDirPieces;          // groups of four columns per piece (this thread owns 32 columns)
-    float4 park[(kDefer && kSplit) ? 8 : 1];     // split modes: the drained pre-activations, in local memory
     const int cdir0 = ch * 32;
     // rgb partial sums go through the dir-embedding buffer: its last readers (the dir-layer MMAs of the tile the sums
     // belong to) have retired, and the encoder warps write the next dir embedding only after rgb_done
     float* rgbp = kSplit ? reinterpret_cast<float*>(s.dir[0]) : s.rgbp_own;     // [4][3][kTile]
-    // piece `pc` of the tile whose row of this thread is point `dpt`; `vreg` = the 32 drained values (kDefer == false)
+    // piece `pc` of the tile whose row of this thread is point `dpt`; `vreg` = the 32 drained values (in-place epilogue)
     auto dir_piece = [&](int pc, long long dpt, const uint32_t* vreg) {
       const int col0 = cdir0 + pc * (4 * kJ4);
       const float4* b4 = reinterpret_cast<const float4*>(s.cst + CL.b[9] + col0);
@@ -993,9 +931,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
         if constexpr (kDirTmem) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(t8[4 * jj + e]);
-        } else if constexpr (kDefer) {
-          const float4 q = park[pc * kJ4 + jj];
-          x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(vreg[4 * jj + e]);
@@ -1003,7 +938,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
         x[0] += bb.x - sh; x[1] += bb.y - sh; x[2] += bb.z - sh; x[3] += bb.w - sh;
         if (new_activation) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) x[e] = SNB_SOFTPLUS_POLY ? softplus_poly<!kSplit>(x[e]) : softplus_fast(x[e]);
+          for (int e = 0; e < 4; ++e) x[e] = softplus_fast(x[e]);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
@@ -1042,18 +977,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
       epi_bar_sync();
       if (lane == 0) mbar_arrive(&s.rgb_done);
     };
-    bool pending = false;      // the previous slot's direction-layer epilogue is still owed (kDefer)
+    bool pending = false;      // the previous slot's direction-layer epilogue is still owed (kDirTmem)
 
     for (long long slot = 0; slot < n_slots; ++slot) {
       const long long pt_slot = tile_of(slot) * kTile + row;
       float sig_part = 0.f;
       // ---------------- trunk epilogues: D (TMEM) -> act -> A (TMEM)
-      // rotated order: layer 1's epilogue of this tile ran at the end of the previous slot (li = 8 there)
-      const bool has_next = rot && slot + 1 < n_slots;
-      const int poff = rot ? 1 : 0;         // first layer of the slot after which a deferred piece runs
-      for (int li = (rot && slot > 0) ? 1 : 0; li < n_layers_epi + (has_next ? 1 : 0); ++li) {
-        const int l = li < n_layers_epi ? li : 0;
-        const long long pt = li < n_layers_epi ? pt_slot : tile_of(slot + 1) * kTile + row;
+      const long long pt = pt_slot;
+      for (int l = 0; l < n_layers_epi; ++l) {
         const float* bias = s.cst + CL.b[l];
         const bool relu = true;
 #pragma unroll 1
@@ -1151,21 +1082,21 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           }
         }
         // ---- background work in the idle window before this layer's next accumulator half is ready
-        if (kDefer && pending && li >= poff && li < poff + kDirPieces) {
+        if (kDirTmem && pending && l < kDirPieces) {
           // the previous tile's direction-layer epilogue, one piece per layer; sigp[0] still holds that tile's sigma
           // (rewritten at l == 7 of this slot)
           const bool trp = (p.debug & 8) && blockIdx.x == 0 && slot == 4 && tid == 0;
           const long long dpt = tile_of(slot - 1) * kTile + row;
-          if (li == poff) trace(trp, 1024 + 18 * 8 + 5);
-          dir_piece(li - poff, dpt, nullptr);
-          if (li - poff == kDirPieces - 1) {
+          if (l == 0) trace(trp, 1024 + 18 * 8 + 5);
+          dir_piece(l, dpt, nullptr);
+          if (l == kDirPieces - 1) {
             trace(trp, 1024 + 18 * 8 + 3);
             dir_finish(dpt);
             pending = false;
             trace(trp, 1024 + 18 * 8 + 4);
           }
         }
-        if (li == 7) {
+        if (l == 7) {
           // sigma head (nerf.py:136): combine the two column halves of each row
           s.sigp[ch][row] = sig_part;
           epi_bar_sync();
@@ -1196,24 +1127,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           tmem_wait_ld();
           tc_fence_before();
           signal(&s.d_drained);      // D[0,128) is in registers: the next slot's layer 1 may overwrite it
-          if constexpr (kDefer) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              park[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                    __uint_as_float(v[4 * j + 3]));
-            pending = true;
-          } else {
-            trace(tr, tb + 2);
-            dir_piece(0, pt_slot, v);
-            trace(tr, tb + 3);
-            dir_finish(pt_slot);
-            trace(tr, tb + 4);
-          }
+          trace(tr, tb + 2);
+          dir_piece(0, pt_slot, v);
+          trace(tr, tb + 3);
+          dir_finish(pt_slot);
+          trace(tr, tb + 4);
         }
-        if (kDefer) trace(tr, tb + 2);
+        if (kDirTmem) trace(tr, tb + 2);
       }
     }
-    if (kDefer && pending) {       // the last slot's direction-layer epilogue
+    if (kDirTmem && pending) {     // the last slot's direction-layer epilogue
       const long long dpt = tile_of(n_slots - 1) * kTile + row;
 #pragma unroll 1
       for (int pc = 0; pc < kDirPieces; ++pc) dir_piece(pc, dpt, nullptr);
