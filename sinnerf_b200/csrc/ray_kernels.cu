@@ -828,32 +828,35 @@ __global__ void __launch_bounds__(128) importance_merge_kernel(
 // image header (snb_refresh_weights).  2.4 MB of L2/HBM reads, one launch; the last block to finish
 // compares, sets header.dirty and resets the scratch fields.
 // ---------------------------------------------------------------------------------------
-constexpr int kCheckBlocks = 64;
+// Grid: 148 blocks x 1024 threads, four words per thread.  (Round 2 launched 64 x 256 -- 36 words per thread, 29 us
+// per model, i.e. 58 us of the 900 us configs[2] patch render, profiles/r02b_timeline_patch_bf16_before.txt; 582 x 256
+// blocks took 16 us: two same-address atomics per block serialise at ~13 ns each.)
+constexpr int kCheckBlocks = 148, kCheckThreads = 1024;
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
   x ^= x >> 27; x *= 0x94d049bb133111ebull;
   return x ^ (x >> 31);
 }
-__global__ void __launch_bounds__(256) params_check_kernel(ParamPtrs pp, int precision, int new_activation,
-                                                           PackedHeader* hdr) {
+__global__ void __launch_bounds__(kCheckThreads) params_check_kernel(ParamPtrs pp, int precision, int new_activation,
+                                                                     PackedHeader* hdr) {
   unsigned long long h = 0;
   unsigned long long base = 0;
   for (int t = 0; t < SNB_N_PARAM_TENSORS; ++t) {
     const int n = param_numel(t);
     const unsigned int* w = reinterpret_cast<const unsigned int*>(pp.p[t]);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
-      h += mix64(((base + e) << 32) ^ (unsigned long long)w[e] ^ 0x9e3779b97f4a7c15ull);
+      h += mix64(((base + e) << 32) ^ (unsigned long long)__ldg(w + e) ^ 0x9e3779b97f4a7c15ull);
     base += n;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(kFull, h, off);
-  __shared__ unsigned long long part[8];
+  __shared__ unsigned long long part[kCheckThreads / 32];
   __shared__ bool last;
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long b = 0;
-    for (int i = 0; i < 8; ++i) b += part[i];
+    for (int i = 0; i < kCheckThreads / 32; ++i) b += part[i];
     atomicAdd(&hdr->partial, b);
     __threadfence();
     last = atomicAdd(&hdr->blocks_done, 1u) == gridDim.x - 1;
@@ -870,7 +873,7 @@ __global__ void __launch_bounds__(256) params_check_kernel(ParamPtrs pp, int pre
 }
 
 int launch_params_check(const ParamPtrs& pp, int precision, int new_activation, void* image, cudaStream_t st) {
-  params_check_kernel<<<kCheckBlocks, 256, 0, st>>>(pp, precision, new_activation, reinterpret_cast<PackedHeader*>(image));
+  params_check_kernel<<<kCheckBlocks, kCheckThreads, 0, st>>>(pp, precision, new_activation, reinterpret_cast<PackedHeader*>(image));
   return check_launch("params_check_kernel");
 }
 

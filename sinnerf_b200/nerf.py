@@ -89,6 +89,7 @@ class NeRF(nn.Module):
             self.sigma = nn.Linear(W, 1)
             self.rgb = nn.Sequential(nn.Linear(W // 2, 3), nn.Sigmoid())
         self._packed = {}  # (precision id, device) -> uint8 device tensor
+        self._fast = {}    # precision id -> validated pointer table of packed_weights()
 
     # ------------------------------------------------------------------ kernels' weight image
     def _check_shape(self):
@@ -98,13 +99,20 @@ class NeRF(nn.Module):
                 "in_channels_dir=27, skips=[4]) -- the shape SinNeRF instantiates (models/sinnerf.py:137,140)")
 
     def _param_list(self):
+        """The 24 parameter tensors in state-dict order.  Walks the module dicts directly (three dict lookups per
+        tensor, ~5 us in all; `getattr` chains through nn.Module.__getattr__ cost 19 us) and always returns the
+        CURRENT Parameter objects, so replaced parameters / sub-modules are seen."""
+        mods = self._modules
         ps = []
         for i in range(self.D):
-            lin = getattr(self, f"xyz_encoding_{i + 1}")[0]
-            ps += [lin.weight, lin.bias]
-        ps += [self.xyz_encoding_final.weight, self.xyz_encoding_final.bias,
-               self.dir_encoding[0].weight, self.dir_encoding[0].bias,
-               self.sigma.weight, self.sigma.bias, self.rgb[0].weight, self.rgb[0].bias]
+            lp = mods[f"xyz_encoding_{i + 1}"]._modules["0"]._parameters
+            ps.append(lp["weight"])
+            ps.append(lp["bias"])
+        for name, sub in (("xyz_encoding_final", None), ("dir_encoding", "0"), ("sigma", None), ("rgb", "0")):
+            m = mods[name] if sub is None else mods[name]._modules[sub]
+            lp = m._parameters
+            ps.append(lp["weight"])
+            ps.append(lp["bias"])
         return ps
 
     def packed_weights(self, precision=None) -> torch.Tensor:
@@ -113,21 +121,36 @@ class NeRF(nn.Module):
         every call enqueues a check kernel that compares a checksum of the parameter VALUES with the one the
         image was packed from and re-packs on the device only when they differ -- so optimizer steps,
         `load_state_dict` and in-place updates through `p.data` (which do not bump `_version`; reference
-        utils/optimizers.py:98,180,268) are all seen, with no host synchronisation."""
+        utils/optimizers.py:98,180,268) are all seen, with no host synchronisation.
+
+        Host cost matters here: a render starts with two of these calls while the GPU idles (a 5 292-ray patch is
+        0.9 ms in all).  The validated pointer table is therefore cached and reused for as long as the 24 storage
+        addresses are the ones it was built from (a dtype / device / layout change re-allocates and is re-validated):
+        ~10 us per call instead of ~70."""
         prec = _lib.precision_id(config.get_precision() if precision is None else precision)
-        image = self.packed_image_buffer(prec)
         ps = self._param_list()
-        dev = ps[0].device
+        ptrs = [p.data_ptr() for p in ps]
+        fast = self._fast.get(prec)
+        if fast is None or fast[0] != ptrs:
+            dev = ps[0].device
+            srcs = []
+            for p in ps:
+                if p.dtype != torch.float32 or p.device != dev:
+                    raise ValueError("NeRF parameters must be fp32 tensors on one CUDA device")
+                srcs.append(p.detach().contiguous())
+            image = self.packed_image_buffer(prec)
+            arr = (C.c_void_p * len(srcs))(*[s.data_ptr() for s in srcs])
+            fast = (ptrs, arr, image, dev, _lib.ptr(image), int(self.use_new_activation))
+            # cache only when the kernels read the parameters' own storage (a non-contiguous parameter is copied per call)
+            self._fast[prec] = fast if all(s.data_ptr() == q for s, q in zip(srcs, ptrs)) else None
+        _, arr, image, dev, image_ptr, new_act = fast
         lib = _lib.load()
-        srcs = []
-        for p in ps:
-            if p.dtype != torch.float32 or p.device != dev:
-                raise ValueError("NeRF parameters must be fp32 tensors on one CUDA device")
-            srcs.append(p.detach().contiguous())
-        arr = (C.c_void_p * len(srcs))(*[s.data_ptr() for s in srcs])
-        with torch.cuda.device(dev):
-            _lib.check(lib.snb_refresh_weights(arr, prec, int(self.use_new_activation), _lib.ptr(image),
-                                               _lib.stream_ptr(dev)), "snb_refresh_weights")
+        if torch.cuda.current_device() == dev.index:
+            _lib.check(lib.snb_refresh_weights(arr, prec, new_act, image_ptr, _lib.stream_ptr(dev)), "snb_refresh_weights")
+        else:
+            with torch.cuda.device(dev):
+                _lib.check(lib.snb_refresh_weights(arr, prec, new_act, image_ptr, _lib.stream_ptr(dev)),
+                           "snb_refresh_weights")
         return image
 
     def packed_image_buffer(self, prec: int) -> torch.Tensor:
@@ -152,6 +175,14 @@ class NeRF(nn.Module):
         """Forget every packed image (they are rebuilt on the next pass).  Never needed for correctness --
         packed_weights() checks the parameter values itself -- only to release the buffers."""
         self._packed = {}
+        self._fast = {}
+
+    def __getstate__(self):
+        # the cached pointer table holds ctypes pointers (not picklable / meaningless in a copy): copy.deepcopy and
+        # torch.save(model) get a module that re-validates on first use
+        d = self.__dict__.copy()
+        d["_fast"] = {}
+        return d
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, sigma_only=False):
