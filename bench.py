@@ -7,7 +7,9 @@ Workload (config.workload): BASELINE.json configs[1] -- a 400x400 lego-shape fra
 synthetic camera rays, N_samples=64 + N_importance=64, 8x256 MLP, fp32-parity arithmetic,
 seeded default-init weights.  One step = one complete render_rays of the frame.
 N > 1 (torchrun, one rank per GPU): weak scaling -- the job is N frames, each rank renders its
-contiguous 160 000-ray slab and the rendered pixels (16 B/ray) are all-gathered over NCCL.
+contiguous 160 000-ray slab and the rendered pixels (16 B/ray) reach every rank -- stored by the
+compositing kernel itself into all ranks' frame buffers (NVSwitch multicast / NVLink P2P, CUDA
+symmetric memory; distributed.PeerPixels), or all-gathered over NCCL with SNB_BENCH_EXCHANGE=nccl.
 
 value  : rays/s, inputs resident in HBM, CUDA-event timed per step (L2 flushed between steps,
          outside the event pairs), max over ranks.
@@ -215,7 +217,7 @@ def workload_config(n_gpus, precision):
     return {"workload": "configs[1]: 400x400 lego-shape frame, 160000 rays/GPU, N_samples=64 N_importance=64, "
                         "8x256 MLP (use_new_activation), perturb=0 noise_std=0 white_back, seeded default-init weights",
             "rays_per_step_per_gpu": 160000, "global_rays_per_step": 160000 * n_gpus, "precision": precision,
-            "parallelism": f"ray-sharded x{n_gpus} + NCCL all-gather of pixels" if n_gpus > 1 else "single GPU",
+            "parallelism": f"ray-sharded x{n_gpus}, the pixels of every slab delivered to every rank" if n_gpus > 1 else "single GPU",
             "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA-event pairs)"}
 
 
@@ -290,28 +292,58 @@ def bench_configs_2(models, emb, dev, lib, flush, sync_all, peaks):
                                   "peak_source": f"MEASURED_PEAKS.json ({peaks['_source']}) bf16_tflops (burst)"}}
 
 
+def make_exchange(rows, rows_per_rank, world, dev):
+    """How the ranks' pixel slabs reach every rank.  Default: the compositing kernel stores them itself into all ranks'
+    frame buffers (CUDA symmetric memory: one NVSwitch multicast address, else NVLink P2P addresses) -- distributed.PeerPixels;
+    SNB_BENCH_EXCHANGE=nccl (or symmetric memory unavailable): the asynchronous NCCL all-gather of round 2 (PixelGather)."""
+    from sinnerf_b200.distributed import PeerPixels, PixelGather
+    if world == 1:
+        return "none", None
+    if os.environ.get("SNB_BENCH_EXCHANGE", "p2p") != "nccl":
+        try:
+            pp = PeerPixels(rows, dev)
+            return ("kernel stores to the NVSwitch multicast address" if pp.multicast else "kernel stores to each peer (NVLink P2P)"), pp
+        except Exception as e:      # noqa: BLE001 -- e.g. no P2P between the devices of this box
+            sys.stderr.write(f"PeerPixels unavailable ({type(e).__name__}: {e}); using the NCCL all-gather\n")
+    return "NCCL all-gather (async, double-buffered)", PixelGather(rows_per_rank, dev)
+
+
 def bench_configs_3_strong(models, emb, dev, rank, world, precision, flush, sync_all):
     """BASELINE configs[3]: ONE 640x512 DTU-shape frame (327 680 rays, 64+64) strong-scaled over the ranks: every rank
     renders its contiguous slab and the pixels are all-gathered (16 B/ray).  The driver forms the speed-up from
     the per-N values."""
     from sinnerf_b200 import rendering, synthetic
-    from sinnerf_b200.distributed import render_rays_sharded
+    from sinnerf_b200.distributed import PeerPixels, render_frame_p2p, render_rays_sharded
     rays = synthetic.frame_rays("dtu", seed=0).to(dev)
     n = rays.shape[0]
+    how, ex = make_exchange(n, -(-n // world), world, dev)
 
-    def render_fn(r):
+    def render_fn(r, sc=None):
         with torch.no_grad():
-            return rendering.render_rays(models, emb, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, True, precision=precision)
+            return rendering.render_rays(models, emb, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, True, precision=precision,
+                                         pixel_scatter=sc)
 
-    def step():
-        return render_rays_sharded(render_fn, rays)
+    if isinstance(ex, PeerPixels):
+        def step():
+            return render_frame_p2p(render_fn, rays, ex)
+
+        def sync3():
+            ex.wait_all()
+            sync_all()
+    else:
+        how = "NCCL all-gather (blocking)" if world > 1 else how
+
+        def step():
+            return render_rays_sharded(render_fn, rays)
+        sync3 = sync_all
     for _ in range(2):
         step()
     iters = 5
-    ms = _timed_steps(step, iters, flush, sync_all, dev, world)
-    return {"workload": "configs[3]: 640x512 DTU-shape frame, 327680 rays, 64+64, rays sharded over the ranks + NCCL all-gather "
-                        "of [rgb, depth] (16 B/ray)", "scaling": "strong", "n_gpus": world, "rays_total": n,
-            "rays_per_rank": -(-n // world), "ms": ms, "rays_per_s": n / (ms / 1e3), "precision": precision, "iters": iters}
+    ms = _timed_steps(step, iters, flush, sync3, dev, world)
+    return {"workload": "configs[3]: 640x512 DTU-shape frame, 327680 rays, 64+64, rays sharded over the ranks, [rgb, depth] "
+                        "(16 B/ray) of every slab delivered to every rank", "exchange": how, "scaling": "strong", "n_gpus": world,
+            "rays_total": n, "rays_per_rank": -(-n // world), "ms": ms, "rays_per_s": n / (ms / 1e3), "precision": precision,
+            "iters": iters}
 
 
 def bench_configs_4_train(dev, rank, local_rank, world, precision, flush, sync_all, NeRF, Embedding, default_init_params):
@@ -431,7 +463,7 @@ def main():
     import torch.distributed as dist
     from sinnerf_b200 import _lib, synthetic
     from sinnerf_b200 import build as _build
-    from sinnerf_b200.distributed import pack_pixels, PixelGather
+    from sinnerf_b200.distributed import pack_pixels, PeerPixels
     from sinnerf_b200.nerf import NeRF, Embedding
     from sinnerf_b200 import rendering
     from oracle.render_oracle import default_init_params  # weights only (seeded init), not on the timed path
@@ -462,16 +494,22 @@ def main():
     rays_pinned = rays_cpu.pin_memory()
     rays_dev = rays_cpu.to(dev)
     pix_host = torch.empty(n, 4).pin_memory()
-    gather = PixelGather(n, dev) if world > 1 else None      # gather k overlaps render k + 1 (no per-step barrier)
+    # every rank's pixels reach every rank: stored by the compositing kernel itself (PeerPixels) or all-gathered (PixelGather);
+    # either way frame k's exchange overlaps render k + 1 (no per-step barrier)
+    exchange_how, gather = make_exchange(n * world, n, world, dev)
+    p2p = isinstance(gather, PeerPixels)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rendering.DRAW_UNUSED_NOISE = True     # keep the reference's randn draws (rendering.py:224)
 
     def step(r):
+        k = gather.begin() if p2p else 0
         with torch.no_grad():
             res = rendering.render_rays(models, emb, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, True,
-                                        precision=precision)
+                                        precision=precision, pixel_scatter=gather.scatter(k, rank * n) if p2p else None)
         pix = pack_pixels(res)
-        if world > 1:
+        if p2p:
+            gather.commit(k)
+        elif world > 1:
             gather.submit(pix)
         return pix
 
@@ -575,6 +613,7 @@ def main():
                       "bf16": "bf16 operands, fp32 accumulate"}[precision],
             "data": "synthetic",
             "config": workload_config(world, precision),
+            "exchange": exchange_how,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 32 * world,
                     "d2h_bytes_per_step": n * 16 * world, "ms_per_step": e2e_ms / args.steps},
             # per render_rays: sample_coarse, field, composite, importance_merge, field, composite + per model the

@@ -116,6 +116,24 @@ int snb_composite_forward(const float* raw, int raw_channels, const float* z_val
                           const float* noise, float noise_std, int white_back, int64_t n_rays,
                           int n_samples, float* rgb, float* depth, float* weights, void* stream);
 
+/* Pixel scatter (multi-GPU inference, SURVEY.md 8e "optional fusion"; the reference has no multi-GPU inference,
+ * eval.py:141-142 -- this replaces the all-gather of rendered pixels that sharding its ray-chunk loop eval.py:92-115
+ * over GPUs needs).  The compositing kernel also stores every ray's [r, g, b, depth] as ONE 16-byte row into up to
+ * SNB_MAX_PIXEL_DST frame buffers at row (row_offset + ray): buffers of peer GPUs mapped into this process (NVLink
+ * P2P / CUDA symmetric memory) or a single NVSwitch multicast address that reaches all of them -- the collective
+ * happens in the kernel's epilogue, no staging copy, no collective kernel.  Visibility on the peers is the caller's
+ * (a cross-device barrier after the kernel; sinnerf_b200/distributed.py: PeerPixels). */
+#define SNB_MAX_PIXEL_DST 8
+typedef struct SnbPixelScatter {
+  void* dst[SNB_MAX_PIXEL_DST];  /* (rows,4) fp32 frame buffers, 16-byte aligned device-accessible addresses */
+  int n_dst;                     /* 1..SNB_MAX_PIXEL_DST                                                       */
+  int64_t row_offset;            /* row of this call's ray 0                                                   */
+} SnbPixelScatter;
+/* snb_composite_forward (raw_channels = 4) + the scatter above. */
+int snb_composite_forward_scatter(const float* raw, const float* z_vals, const float* rays, const float* noise,
+                                  float noise_std, int white_back, int64_t n_rays, int n_samples, float* rgb,
+                                  float* depth, float* weights, const SnbPixelScatter* scatter, void* stream);
+
 /* sample_pdf, models/rendering.py:15-61.  bins (N,M+1) row stride bins_stride; weights (N,M) row
  * stride w_stride; u: det -> (n_importance,) = torch.linspace(0,1,n_importance) with u_stride 0,
  * else (N,n_importance) with u_stride n_importance.  -> samples (N,n_importance). */
@@ -269,6 +287,7 @@ typedef struct SnbRenderArgs {
   float* rgb_fine;          /* (N,3)                                                    */
   float* depth_fine;        /* (N,)                                                     */
   float* weights_fine;      /* (N,S+Ni)                                                 */
+  const SnbPixelScatter* pixel_scatter; /* NULL, or: the last pass's compositing also scatters [rgb, depth] rows */
 } SnbRenderArgs;
 
 /* render_rays forward, models/rendering.py:126-335, as one call: every stage above enqueued

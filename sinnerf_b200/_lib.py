@@ -20,6 +20,13 @@ PRECISIONS = {"fp32": 0, "f16x3": 1, "bf16x3": 2, "bf16": 3}
 c_f = C.c_void_p  # device pointers travel as void*
 
 
+MAX_PIXEL_DST = 8   # SNB_MAX_PIXEL_DST
+
+
+class SnbPixelScatter(C.Structure):
+    _fields_ = [("dst", c_f * MAX_PIXEL_DST), ("n_dst", C.c_int), ("row_offset", C.c_int64)]
+
+
 class SnbRenderArgs(C.Structure):
     _fields_ = [
         ("rays", c_f), ("n_rays", C.c_int64), ("n_samples", C.c_int), ("n_importance", C.c_int),
@@ -28,7 +35,7 @@ class SnbRenderArgs(C.Structure):
         ("z_steps", c_f), ("u_steps", c_f), ("perturb_u", c_f), ("noise_coarse", c_f), ("pdf_u", c_f),
         ("noise_fine", c_f), ("z_coarse", c_f), ("raw_coarse", c_f), ("rgb_coarse", c_f),
         ("depth_coarse", c_f), ("weights_coarse", c_f), ("z_fine", c_f), ("raw_fine", c_f),
-        ("rgb_fine", c_f), ("depth_fine", c_f), ("weights_fine", c_f),
+        ("rgb_fine", c_f), ("depth_fine", c_f), ("weights_fine", c_f), ("pixel_scatter", C.POINTER(SnbPixelScatter)),
     ]
 
 
@@ -59,6 +66,8 @@ SIGNATURES = {
     "snb_field_forward": (C.c_int, [c_f, C.c_int, c_f, c_f, C.c_int64, C.c_int, C.c_int, c_f, c_f]),
     "snb_composite_forward": (C.c_int, [c_f, C.c_int, c_f, c_f, c_f, C.c_float, C.c_int, C.c_int64, C.c_int,
                                         c_f, c_f, c_f, c_f]),
+    "snb_composite_forward_scatter": (C.c_int, [c_f, c_f, c_f, c_f, C.c_float, C.c_int, C.c_int64, C.c_int,
+                                                c_f, c_f, c_f, C.POINTER(SnbPixelScatter), c_f]),
     "snb_sample_pdf": (C.c_int, [c_f, C.c_int64, c_f, C.c_int64, c_f, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                  C.c_float, c_f, c_f]),
     "snb_importance_merge": (C.c_int, [c_f, c_f, c_f, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_float, c_f,

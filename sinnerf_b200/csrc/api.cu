@@ -43,7 +43,7 @@ int sm_count() {
 int launch_sample_coarse(const float*, const float*, const float*, float, int, int64_t, int, float*, cudaStream_t);
 int launch_embed(const float*, int64_t, int, int, float*, cudaStream_t);
 int launch_composite(const float*, int, const float*, const float*, const float*, float, int, int64_t, int,
-                     float*, float*, float*, const SnbLossSpec*, float*, float*, cudaStream_t);
+                     float*, float*, float*, const SnbLossSpec*, float*, float*, const SnbPixelScatter*, cudaStream_t);
 int launch_sample_pdf(const float*, int64_t, const float*, int64_t, const float*, int64_t, int64_t, int, int,
                       float, float*, cudaStream_t);
 int launch_importance_merge(const float*, const float*, const float*, int64_t, int64_t, int, int, float, float*,
@@ -191,7 +191,23 @@ int snb_composite_forward(const float* raw, int raw_channels, const float* z_val
   SNB_REQUIRE(raw_channels == 1 || aligned16(raw), "snb_composite_forward: raw must be 16-byte aligned");
   const float* nz = (noise_std != 0.f) ? noise : nullptr;
   return launch_composite(raw, raw_channels, z_vals, rays, nz, noise_std, white_back, n_rays, n_samples, rgb,
-                          depth, weights, nullptr, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream));
+                          depth, weights, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int snb_composite_forward_scatter(const float* raw, const float* z_vals, const float* rays, const float* noise,
+                                  float noise_std, int white_back, int64_t n_rays, int n_samples, float* rgb,
+                                  float* depth, float* weights, const SnbPixelScatter* scatter, void* stream) {
+  SNB_REQUIRE(n_rays >= 0 && n_samples >= 1, "snb_composite_forward_scatter: bad extents");
+  SNB_REQUIRE(n_rays == 0 || (raw && z_vals && rays && weights && rgb && depth), "snb_composite_forward_scatter: null pointer");
+  SNB_REQUIRE(aligned16(raw), "snb_composite_forward_scatter: raw must be 16-byte aligned");
+  SNB_REQUIRE(scatter != nullptr && scatter->n_dst >= 1 && scatter->n_dst <= SNB_MAX_PIXEL_DST && scatter->row_offset >= 0,
+              "snb_composite_forward_scatter: scatter needs 1..%d destinations and a non-negative row offset", SNB_MAX_PIXEL_DST);
+  for (int i = 0; i < scatter->n_dst; ++i)
+    SNB_REQUIRE(scatter->dst[i] != nullptr && aligned16(scatter->dst[i]),
+                "snb_composite_forward_scatter: destination %d is null or not 16-byte aligned", i);
+  const float* nz = (noise_std != 0.f) ? noise : nullptr;
+  return launch_composite(raw, 4, z_vals, rays, nz, noise_std, white_back, n_rays, n_samples, rgb, depth, weights,
+                          nullptr, nullptr, nullptr, scatter, reinterpret_cast<cudaStream_t>(stream));
 }
 
 static int check_loss_spec(const char* who, const SnbLossSpec* loss) {
@@ -211,7 +227,7 @@ int snb_composite_forward_loss(const float* raw, const float* z_vals, const floa
   SNB_REQUIRE(aligned16(raw), "snb_composite_forward_loss: raw must be 16-byte aligned");
   const float* nz = (noise_std != 0.f) ? noise : nullptr;
   return launch_composite(raw, 4, z_vals, rays, nz, noise_std, white_back, n_rays, n_samples, rgb, depth, weights,
-                          loss, loss_out, loss_ws, reinterpret_cast<cudaStream_t>(stream));
+                          loss, loss_out, loss_ws, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int snb_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride, const float* u,
@@ -373,6 +389,10 @@ int snb_render_forward(const SnbRenderArgs* a, void* stream) {
   if ((rc = snb_field_forward(a->packed_coarse, a->precision, a->rays, a->z_coarse, a->n_rays, S, a->test_time,
                               a->raw_coarse, stream)))
     return rc;
+  if (Ni == 0 && a->pixel_scatter != nullptr)     // the coarse pass is the last one: its pixels are the frame's
+    return snb_composite_forward_scatter(a->raw_coarse, a->z_coarse, a->rays, a->noise_coarse, a->noise_std, a->white_back,
+                                         a->n_rays, S, a->rgb_coarse, a->depth_coarse, a->weights_coarse, a->pixel_scatter,
+                                         stream);
   if ((rc = snb_composite_forward(a->raw_coarse, a->test_time ? 1 : 4, a->z_coarse, a->rays, a->noise_coarse,
                                   a->noise_std, a->white_back, a->n_rays, S, a->rgb_coarse, a->depth_coarse,
                                   a->weights_coarse, stream)))
@@ -389,6 +409,10 @@ int snb_render_forward(const SnbRenderArgs* a, void* stream) {
   if ((rc = snb_field_forward(a->packed_fine, a->precision, a->rays, a->z_fine, a->n_rays, S + Ni, 0, a->raw_fine,
                               stream)))
     return rc;
+  if (a->pixel_scatter != nullptr)
+    return snb_composite_forward_scatter(a->raw_fine, a->z_fine, a->rays, a->noise_fine, a->noise_std, a->white_back,
+                                         a->n_rays, S + Ni, a->rgb_fine, a->depth_fine, a->weights_fine, a->pixel_scatter,
+                                         stream);
   return snb_composite_forward(a->raw_fine, 4, a->z_fine, a->rays, a->noise_fine, a->noise_std, a->white_back,
                                a->n_rays, S + Ni, a->rgb_fine, a->depth_fine, a->weights_fine, stream);
 }

@@ -184,6 +184,16 @@ struct LossSpec {
   const float* wd;       // (N,) nullable -> wd0
   float wr0, wd0;
 };
+// [r, g, b, depth] rows of the rays into frame buffers that may live on other GPUs (include/sinnerf_b200.h: SnbPixelScatter)
+struct PixelScatter {
+  float4* dst[SNB_MAX_PIXEL_DST];
+  int n;
+  long long off;
+};
+__device__ __forceinline__ void scatter_pixel(const PixelScatter& ps, long long ray, float r, float g, float b, float d) {
+  const float4 px = make_float4(r, g, b, d);
+  for (int i = 0; i < ps.n; ++i) ps.dst[i][ps.off + ray] = px;   // plain stores: P2P-mapped or multicast addresses
+}
 __device__ __forceinline__ float smooth_l1(float x) { const float a = fabsf(x); return a < 1.0f ? 0.5f * x * x : a - 0.5f; }
 __device__ __forceinline__ float smooth_l1_grad(float x) { return fabsf(x) < 1.0f ? x : (x > 0.f ? 1.0f : -1.0f); }
 
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(
     const float* __restrict__ raw, int raw_channels, const float* __restrict__ z_vals,
     const float* __restrict__ rays, const float* __restrict__ noise, float noise_std, int white_back,
     long long n_rays, int S, float* __restrict__ rgb_out, float* __restrict__ depth_out,
-    float* __restrict__ w_out, LossSpec ls, float* __restrict__ loss_out, float* __restrict__ loss_ws) {
+    float* __restrict__ w_out, LossSpec ls, float* __restrict__ loss_out, float* __restrict__ loss_ws, PixelScatter ps) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -266,6 +276,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(
           if (ls.tdepth != nullptr)
             loss_depth = fmaf(ls.wd != nullptr ? ls.wd[ray] : ls.wd0, smooth_l1(ad - ls.tdepth[ray]), loss_depth);
         }
+        if (ps.n > 0) scatter_pixel(ps, ray, ar, ag, ab, ad);
       }
     }
   }
@@ -465,7 +476,7 @@ __global__ void __launch_bounds__(256) composite_fwd4_kernel(
     const float* __restrict__ raw, int raw_channels, const float* __restrict__ z_vals,
     const float* __restrict__ rays, const float* __restrict__ noise, float noise_std, int white_back,
     long long n_rays, int S, float* __restrict__ rgb_out, float* __restrict__ depth_out,
-    float* __restrict__ w_out, LossSpec ls, float* __restrict__ loss_out, float* __restrict__ loss_ws) {
+    float* __restrict__ w_out, LossSpec ls, float* __restrict__ loss_out, float* __restrict__ loss_ws, PixelScatter ps) {
   constexpr int kRpw = 32 / L;
   const int lane = threadIdx.x & 31, sl = lane & (L - 1), sub = lane / L;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -533,6 +544,7 @@ __global__ void __launch_bounds__(256) composite_fwd4_kernel(
           if (ls.tdepth != nullptr)
             loss_depth = fmaf(ls.wd != nullptr ? ls.wd[ray] : ls.wd0, smooth_l1(ad - ls.tdepth[ray]), loss_depth);
         }
+        if (ps.n > 0) scatter_pixel(ps, ray, ar, ag, ab, ad);
       }
     }
   }
@@ -983,7 +995,14 @@ static LossSpec make_loss_spec(const SnbLossSpec* l) {
 
 int launch_composite(const float* raw, int raw_channels, const float* z, const float* rays, const float* noise,
                      float noise_std, int white_back, int64_t n_rays, int S, float* rgb, float* depth,
-                     float* w, const SnbLossSpec* loss, float* loss_out, float* loss_ws, cudaStream_t st) {
+                     float* w, const SnbLossSpec* loss, float* loss_out, float* loss_ws, const SnbPixelScatter* scatter,
+                     cudaStream_t st) {
+  PixelScatter ps{};
+  if (scatter != nullptr) {
+    ps.n = scatter->n_dst;
+    ps.off = scatter->row_offset;
+    for (int i = 0; i < ps.n; ++i) ps.dst[i] = reinterpret_cast<float4*>(scatter->dst[i]);
+  }
   if (n_rays == 0) {
     if (loss_out != nullptr) return cudaMemsetAsync(loss_out, 0, 2 * sizeof(float), st) == cudaSuccess
                                         ? SNB_OK : fail(SNB_ERR_CUDA, "cudaMemsetAsync(loss)");
@@ -996,15 +1015,15 @@ int launch_composite(const float* raw, int raw_channels, const float* z, const f
     int grid = grid_for(n_rays, 8 * (32 / L), device_sms() * 8);
     if (loss_out != nullptr && grid > (SNB_LOSS_WS_FLOATS - 4) / 2) grid = (SNB_LOSS_WS_FLOATS - 4) / 2;
     const LossSpec ls = make_loss_spec(loss);
-    if (L == 8) composite_fwd4_kernel<8><<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays, S, rgb, depth, w, ls, loss_out, loss_ws);
-    else if (L == 16) composite_fwd4_kernel<16><<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays, S, rgb, depth, w, ls, loss_out, loss_ws);
-    else composite_fwd4_kernel<32><<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays, S, rgb, depth, w, ls, loss_out, loss_ws);
+    if (L == 8) composite_fwd4_kernel<8><<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays, S, rgb, depth, w, ls, loss_out, loss_ws, ps);
+    else if (L == 16) composite_fwd4_kernel<16><<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays, S, rgb, depth, w, ls, loss_out, loss_ws, ps);
+    else composite_fwd4_kernel<32><<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays, S, rgb, depth, w, ls, loss_out, loss_ws, ps);
     return check_launch("composite_fwd4_kernel");
   }
   int grid = grid_for(n_rays, 8, device_sms() * 8);
   if (loss_out != nullptr && grid > (SNB_LOSS_WS_FLOATS - 4) / 2) grid = (SNB_LOSS_WS_FLOATS - 4) / 2;
   composite_fwd_kernel<<<grid, 256, 0, st>>>(raw, raw_channels, z, rays, noise, noise_std, white_back, n_rays,
-                                             S, rgb, depth, w, make_loss_spec(loss), loss_out, loss_ws);
+                                             S, rgb, depth, w, make_loss_spec(loss), loss_out, loss_ws, ps);
   return check_launch("composite_fwd_kernel");
 }
 

@@ -82,3 +82,100 @@ class PixelGather:
             if w is not None:
                 w.wait()
                 self.works[i] = None
+
+
+class PeerPixels:
+    """Rendered pixels written straight into every rank's frame buffer by the compositing kernel (SURVEY 8e's
+    "optional fusion"): no collective kernel, no staging copy -- the all-gather IS the kernel's epilogue.
+
+    Every rank owns `depth` frame buffers ((rows, 4) fp32 [r, g, b, depth]) in CUDA symmetric memory
+    (`torch.distributed._symmetric_memory`): each is mapped into every peer process, and on NVSwitch systems also behind
+    ONE multicast address whose stores the switch replicates to all ranks.  `render_rays(..., pixel_scatter=
+    pp.scatter(k, row0))` hands those addresses to `composite_fwd4_kernel`, whose output lane stores the ray's row to the
+    multicast address (one 16-byte store per ray) or to each peer in turn.  What remains of the collective is a
+    device-side barrier per frame, run on a side stream:
+
+        k = pp.begin()                                    # frame index; waits (stream-level) until its buffer is free
+        render_rays(..., pixel_scatter=pp.scatter(k, lo)) # this rank's slab, rows [lo, hi)
+        pp.commit(k)                                      # side stream: barrier among the ranks after this render
+        frame = pp.frame(k)                               # (rows, 4): current stream waits for that barrier
+
+    Buffer reuse: frame k and k + depth share a buffer.  A rank renders frame j only after the barrier of frame j - 2
+    has completed; its own arrival at that barrier is enqueued behind its render of frame j - 2, and reads of frame k
+    must be enqueued (current stream) before `begin()` of frame k + 2 -- so with depth = 4 every peer's reads of frame k
+    precede any store of frame k + 4, while a rank may run up to two frames ahead of the slowest one (no per-frame
+    lockstep: the round-1 all-gather cost 4 % at 8 power-capped GPUs that way)."""
+
+    def __init__(self, rows: int, device, group: Optional[dist.ProcessGroup] = None, depth: int = 4,
+                 multicast: Optional[bool] = None):
+        import torch.distributed._symmetric_memory as symm
+        if depth < 4:
+            raise ValueError("PeerPixels needs depth >= 4 (see the buffer-reuse rule in the class docstring)")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.device = torch.device(device)
+        self.rows = rows
+        self.bufs, self.hdls = [], []
+        for _ in range(depth):
+            t = symm.empty(rows, 4, dtype=torch.float32, device=self.device)
+            self.hdls.append(symm.rendezvous(t, self.group))
+            self.bufs.append(t)
+        have_mc = all(int(h.multicast_ptr) != 0 for h in self.hdls)
+        self.multicast = have_mc if multicast is None else (bool(multicast) and have_mc)
+        self.side = torch.cuda.Stream(self.device)
+        self.done: list = [None] * depth        # event: the barrier after the last render into this buffer has completed
+        self.k = 0
+
+    def begin(self) -> int:
+        k = self.k
+        self.k += 1
+        j = k - 2
+        if j >= 0 and self.done[j % len(self.bufs)] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.done[j % len(self.bufs)])
+        return k
+
+    def scatter(self, k: int, row_offset: int):
+        """(destination addresses, row offset) for render_rays(pixel_scatter=...)."""
+        h = self.hdls[k % len(self.bufs)]
+        dsts = [int(h.multicast_ptr)] if self.multicast else [int(p) for p in h.buffer_ptrs]
+        return dsts, row_offset
+
+    def commit(self, k: int) -> None:
+        i = k % len(self.bufs)
+        main = torch.cuda.current_stream(self.device)
+        rendered = torch.cuda.Event()
+        rendered.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(rendered)
+            self.hdls[i].barrier(channel=0)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[i] = ev
+
+    def frame(self, k: int) -> torch.Tensor:
+        i = k % len(self.bufs)
+        if self.done[i] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.done[i])
+        return self.bufs[i]
+
+    def wait_all(self) -> None:
+        main = torch.cuda.current_stream(self.device)
+        for ev in self.done:
+            if ev is not None:
+                main.wait_event(ev)
+
+
+def render_frame_p2p(render_fn, rays: torch.Tensor, pixels: PeerPixels) -> torch.Tensor:
+    """`render_rays_sharded` without the collective: this rank's slab of `rays` (the same (N,8) tensor on every rank) is
+    rendered by `render_fn(rays_slab, pixel_scatter)` -- e.g. `lambda r, sc: render_rays(models, emb, r, ...,
+    pixel_scatter=sc)` -- whose last compositing kernel stores the pixels into every rank's frame buffer.  Returns the
+    (N,4) frame [r, g, b, depth] (valid on the current stream; see PeerPixels for how long)."""
+    n = rays.shape[0]
+    if n > pixels.rows:
+        raise ValueError(f"render_frame_p2p: {n} rays, frame buffers of {pixels.rows} rows")
+    lo, hi = shard_bounds(n, pixels.world, pixels.rank)
+    k = pixels.begin()
+    if hi > lo:
+        render_fn(rays[lo:hi], pixels.scatter(k, lo))
+    pixels.commit(k)
+    return pixels.frame(k)[:n]

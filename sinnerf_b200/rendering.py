@@ -397,6 +397,7 @@ def render_rays(models,
                 *,
                 precision: Optional[str] = None,
                 losses: Optional[RayLosses] = None,
+                pixel_scatter=None,
                 _rng: Optional[Dict[str, torch.Tensor]] = None,
                 _return_intermediates: bool = False,
                 ):
@@ -414,6 +415,8 @@ def render_rays(models,
     sinnerf_b200.config; `losses` (a RayLosses, training path only) evaluates the MSE-rgb / SmoothL1-depth
     terms of models/sinnerf.py:310-319 inside the compositing kernels and adds `loss_rgb`, `loss_depth`
     (0-dim, differentiable; coarse + fine) and `loss_coarse` / `loss_fine` ((2,) each) to the result;
+    `pixel_scatter` (inference only; `(destination addresses, row offset)`, see distributed.PeerPixels) makes the last
+    pass's compositing kernel also store each ray's [r, g, b, depth] row into frame buffers on other GPUs;
     `_rng` injects the four random tensors (tests).
     """
     if len(embeddings) != 2 or (embeddings[0].N_freqs, embeddings[0].in_channels) != (10, 3) or \
@@ -446,6 +449,8 @@ def render_rays(models,
         return t.to(dev, torch.float32).contiguous()
 
     if _needs_grad(models[:2 if Ni > 0 else 1]):
+        if pixel_scatter is not None:
+            raise ValueError("render_rays(pixel_scatter=...) is an inference feature: call it under torch.no_grad()")
         if test_time:
             raise NotImplementedError("render_rays(test_time=True) under autograd is not built (the reference "
                                       "never trains with it: models/sinnerf.py:176-186)")
@@ -453,6 +458,17 @@ def render_rays(models,
                                   bool(detach_coarse), rnd, _return_intermediates, prec, losses)
     if losses is not None:
         raise ValueError("render_rays(losses=...) is the training path: it needs grad mode and trainable NeRF parameters")
+    scatter = None
+    if pixel_scatter is not None:
+        if test_time:
+            raise ValueError("render_rays(pixel_scatter=...) needs rgb / depth of the last pass: not with test_time")
+        dsts, row_offset = pixel_scatter
+        if not 1 <= len(dsts) <= _lib.MAX_PIXEL_DST:
+            raise ValueError(f"pixel_scatter: 1..{_lib.MAX_PIXEL_DST} destinations, got {len(dsts)}")
+        scatter = _lib.SnbPixelScatter()
+        for i, d in enumerate(dsts):
+            scatter.dst[i] = int(d)
+        scatter.n_dst, scatter.row_offset = len(dsts), int(row_offset)
 
     # random draws in the reference's order (rendering.py:281, :224, :43, :224)
     perturb_u = rnd("perturb_u", torch.rand, n, S) if perturb > 0 else None
@@ -493,6 +509,8 @@ def render_rays(models,
         a.rgb_fine, a.depth_fine, a.weights_fine = _lib.ptr(rgb_f), _lib.ptr(depth_f), _lib.ptr(w_f)
         keep += [img_f, u_steps, pdf_u, noise_f]
 
+    if scatter is not None:
+        a.pixel_scatter = C.pointer(scatter)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().snb_render_forward(C.byref(a), _lib.stream_ptr(dev)), "snb_render_forward")
 

@@ -53,6 +53,12 @@ def test_argument_validation_without_gpu(lib):
     rc = lib.snb_importance_merge(None, None, None, 0, 4, 2, 8, 1e-5, None, None, None)
     assert rc == -1 and b"N_samples >= 3" in lib.snb_last_error()
     assert lib.snb_render_forward(None, None) == -1
+    rc = lib.snb_composite_forward_scatter(None, None, None, None, 0.0, 0, 0, 64, None, None, None, None, None)
+    assert rc == -1 and b"scatter" in lib.snb_last_error()
+    sc = _lib.SnbPixelScatter()
+    sc.n_dst = _lib.MAX_PIXEL_DST + 1
+    rc = lib.snb_composite_forward_scatter(None, None, None, None, 0.0, 0, 0, 64, None, None, None, C.byref(sc), None)
+    assert rc == -1 and b"destinations" in lib.snb_last_error()
     a = _lib.SnbRenderArgs()
     a.n_rays = 0
     a.n_samples = 64

@@ -357,6 +357,36 @@ def test_second_device_in_one_process():
     assert rel_l2(outs[1][1], outs[0][1]) <= 1e-5
 
 
+# ------------------------------------------------------------------------------------------ pixel scatter (multi-GPU epilogue)
+@pytest.mark.parametrize("n_importance", [64, 0])
+def test_pixel_scatter_rows_equal_outputs(n_importance):
+    """render_rays(pixel_scatter=...): the last pass's compositing kernel also stores [r, g, b, depth] rows into the given
+    frame buffers at (row offset + ray) -- here two local buffers stand in for peer GPUs' memory (the 2-GPU run of
+    tools/p2p_check.py covers NVLink / multicast addresses).  Rows outside the slab stay untouched; the regular outputs
+    are bit-identical to a call without the scatter."""
+    from sinnerf_b200.rendering import render_rays
+    pc, pf = orc.default_init_params(0), orc.default_init_params(1)
+    models = make_models(pc, pf)
+    n, off = 333, 57          # odd count: ragged last warp pass of the four-samples-per-thread kernel
+    case = load_npz("render_llff_room_64p64_train.npz")
+    base = torch.from_numpy(case["rays"].copy())
+    rays = base[torch.arange(n) % base.shape[0]].clone().to(DEV)
+    bufs = [torch.full((n + 100, 4), -7.0, device=DEV) for _ in range(2)]
+    with torch.no_grad():
+        ref = render_rays(models, embeddings(), rays, 64, False, 0, 0, n_importance, 32768, True)
+        out = render_rays(models, embeddings(), rays, 64, False, 0, 0, n_importance, 32768, True,
+                          pixel_scatter=([b.data_ptr() for b in bufs], off))
+    torch.cuda.synchronize()
+    for k in ("rgb_coarse", "depth_coarse", "rgb_fine", "depth_fine", "opacity_fine"):
+        assert torch.equal(out[k], ref[k]), k
+    want = torch.cat([out["rgb_fine"], out["depth_fine"][:, None]], dim=1)
+    for b in bufs:
+        assert torch.equal(b[off:off + n], want)
+        assert bool((b[:off] == -7.0).all()) and bool((b[off + n:] == -7.0).all())
+    with pytest.raises(ValueError):
+        render_rays(models, embeddings(), rays, 64, False, 0, 0, n_importance, 32768, True, pixel_scatter=([], 0))
+
+
 # ------------------------------------------------------------------------------------------ 16-bit training storage
 @pytest.mark.parametrize("weights,n_rays,train_noise", [("seed", 256, False), ("room", 256, True), ("seed", 1500, True)])
 def test_fp16_training_storage_matches_fp32_storage_and_oracle(weights, n_rays, train_noise):
