@@ -90,6 +90,7 @@ class NeRF(nn.Module):
             self.rgb = nn.Sequential(nn.Linear(W // 2, 3), nn.Sigmoid())
         self._packed = {}  # (precision id, device) -> uint8 device tensor
         self._fast = {}    # precision id -> validated pointer table of packed_weights()
+        self._last_stream = {}   # precision id -> the stream the image was last refreshed / read on
 
     # ------------------------------------------------------------------ kernels' weight image
     def _check_shape(self):
@@ -145,12 +146,20 @@ class NeRF(nn.Module):
             self._fast[prec] = fast if all(s.data_ptr() == q for s, q in zip(srcs, ptrs)) else None
         _, arr, image, dev, image_ptr, new_act = fast
         lib = _lib.load()
+        # the image (and its header's check scratch) is shared by every stream that renders with this model: when the
+        # stream changes, the new one first waits for what the previous one had enqueued (the image used to be
+        # packed on the stream of first use and read from others with no ordering)
+        stream = torch.cuda.current_stream(dev)
+        last = self._last_stream.get(prec)
+        if last is not None and last != stream:
+            stream.wait_stream(last)
+        self._last_stream[prec] = stream
+        sp = C.c_void_p(stream.cuda_stream)
         if torch.cuda.current_device() == dev.index:
-            _lib.check(lib.snb_refresh_weights(arr, prec, new_act, image_ptr, _lib.stream_ptr(dev)), "snb_refresh_weights")
+            _lib.check(lib.snb_refresh_weights(arr, prec, new_act, image_ptr, sp), "snb_refresh_weights")
         else:
             with torch.cuda.device(dev):
-                _lib.check(lib.snb_refresh_weights(arr, prec, new_act, image_ptr, _lib.stream_ptr(dev)),
-                           "snb_refresh_weights")
+                _lib.check(lib.snb_refresh_weights(arr, prec, new_act, image_ptr, sp), "snb_refresh_weights")
         return image
 
     def packed_image_buffer(self, prec: int) -> torch.Tensor:
@@ -176,12 +185,14 @@ class NeRF(nn.Module):
         packed_weights() checks the parameter values itself -- only to release the buffers."""
         self._packed = {}
         self._fast = {}
+        self._last_stream = {}
 
     def __getstate__(self):
         # the cached pointer table holds ctypes pointers (not picklable / meaningless in a copy): copy.deepcopy and
         # torch.save(model) get a module that re-validates on first use
         d = self.__dict__.copy()
         d["_fast"] = {}
+        d["_last_stream"] = {}
         return d
 
     # ------------------------------------------------------------------ forward

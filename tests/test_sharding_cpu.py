@@ -96,3 +96,52 @@ def test_pixel_gather_double_buffering(tmp_path):
         for f, buf in seen:
             assert buf.shape == (10, 4)
             assert torch.equal(buf[:5], torch.full((5, 4), float(10 * f))) and torch.equal(buf[5:], torch.full((5, 4), float(10 * f + 1)))
+
+
+class _FakePeerPixels:
+    """The protocol of distributed.PeerPixels with ONE shared CPU buffer per frame slot standing in for the symmetric
+    memory of all ranks (the stores that the CUDA kernel makes are done by the fake render function below)."""
+
+    def __init__(self, rows, world, rank, shared):
+        self.rows, self.world, self.rank, self.bufs = rows, world, rank, shared
+        self.k, self.log = 0, []
+
+    def begin(self):
+        self.k += 1
+        self.log.append(("begin", self.k - 1))
+        return self.k - 1
+
+    def scatter(self, k, row_offset):
+        return [("slot", k % len(self.bufs))], row_offset
+
+    def commit(self, k):
+        self.log.append(("commit", k))
+
+    def frame(self, k):
+        self.log.append(("frame", k))
+        return self.bufs[k % len(self.bufs)]
+
+
+def test_render_frame_p2p_places_every_slab_and_keeps_the_call_order():
+    """render_frame_p2p = begin -> render own slab with (destinations, row offset of the slab) -> commit -> frame; the
+    ranks' slabs tile the frame exactly (ragged tail included) and rows past the frame are never written."""
+    from sinnerf_b200.distributed import render_frame_p2p
+    for n, world in ((10, 3), (9, 4), (5, 8), (64, 2)):
+        shared = [torch.full((n + 3, 4), -1.0) for _ in range(4)]
+        rays = torch.arange(n * 8, dtype=torch.float32).reshape(n, 8)
+        pps = [_FakePeerPixels(n + 3, world, r, shared) for r in range(world)]
+        for frame_no in range(3):
+            outs = []
+            for r in range(world):
+                def render(slab, sc, r=r):
+                    (dst,), off = sc
+                    assert dst == ("slot", frame_no % 4)
+                    shared[dst[1]][off:off + slab.shape[0]] = slab[:, :4] + 100.0 * frame_no     # what the kernel's stores do
+                outs.append(render_frame_p2p(render, rays, pps[r]))
+            for o in outs:
+                assert o.shape == (n, 4) and torch.equal(o, rays[:, :4] + 100.0 * frame_no)
+            assert bool((shared[frame_no % 4][n:] == -1.0).all())
+        for pp in pps:
+            assert pp.log == [(w, k) for k in range(3) for w in ("begin", "commit", "frame")]
+    with pytest.raises(ValueError):
+        render_frame_p2p(lambda slab, sc: None, torch.zeros(20, 8), _FakePeerPixels(10, 2, 0, [torch.zeros(10, 4)] * 4))
