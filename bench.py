@@ -466,7 +466,7 @@ def main():
     from sinnerf_b200.distributed import pack_pixels, PeerPixels
     from sinnerf_b200.nerf import NeRF, Embedding
     from sinnerf_b200 import rendering
-    from oracle.render_oracle import default_init_params  # weights only (seeded init), not on the timed path
+    from sinnerf_b200.synthetic import default_init_params  # noqa: E402  (seeded default-init weights)
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     if world > 1:

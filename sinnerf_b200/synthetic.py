@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
+from typing import Dict
 
 import torch
 
@@ -96,3 +97,16 @@ def random_rays(shape: str, n: int, seed: int = 0) -> torch.Tensor:
     gen = torch.Generator().manual_seed(seed + 104729)
     idx = torch.randint(0, fs.width * fs.height, (n,), generator=gen)
     return allr[idx].contiguous()
+
+
+def default_init_params(seed: int) -> Dict[str, torch.Tensor]:
+    """State dict of `torch.manual_seed(seed); NeRF(use_new_activation=True)` -- the seeded default-init weights the bench
+    and the measurement tools render with (the modules are created in the reference's order, models/nerf.py:66-103, so
+    these are the reference's numbers; tests/test_oracle_golden.py holds them equal to the oracle's own copy).  The global
+    RNG state is left untouched."""
+    from .nerf import NeRF
+    state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    sd = {k: v.detach().clone() for k, v in NeRF(use_new_activation=True).state_dict().items()}
+    torch.random.set_rng_state(state)
+    return sd

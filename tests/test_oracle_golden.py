@@ -142,3 +142,17 @@ def test_camera_rays_match_reference():
     got = orc.camera_rays(int(H), int(W), (float(fx), float(fy)), t(gz["dtu_c2w"]), near, far, center=(float(cx), float(cy)),
                           opencv=True)
     assert torch.allclose(got, t(gz["dtu_rays"]), rtol=0, atol=1e-6)
+
+
+def test_synthetic_default_init_equals_the_oracles():
+    """bench.py and tools/ take their seeded weights from sinnerf_b200.synthetic (the product side must not import the
+    oracle); they are the same numbers as the oracle's restatement of the reference's default init."""
+    import torch
+    from oracle import render_oracle as orc
+    from sinnerf_b200 import synthetic
+    before = torch.random.get_rng_state()
+    for seed in (0, 1, 5):
+        a, b = synthetic.default_init_params(seed), orc.default_init_params(seed)
+        assert list(a) == list(b)
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(before, torch.random.get_rng_state())

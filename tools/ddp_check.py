@@ -14,7 +14,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 from torch.nn.parallel import DistributedDataParallel as DDP  # noqa: E402
 
-from oracle.render_oracle import default_init_params  # noqa: E402  (seeded weights only)
+from sinnerf_b200.synthetic import default_init_params  # noqa: E402  (seeded default-init weights)
 from sinnerf_b200 import synthetic  # noqa: E402
 from sinnerf_b200.nerf import NeRF, Embedding  # noqa: E402
 from sinnerf_b200.rendering import render_rays  # noqa: E402

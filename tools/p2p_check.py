@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from oracle.render_oracle import default_init_params  # noqa: E402  (seeded weights only)
+from sinnerf_b200.synthetic import default_init_params  # noqa: E402  (seeded default-init weights)
 from sinnerf_b200 import synthetic  # noqa: E402
 from sinnerf_b200.distributed import PeerPixels, PixelGather, pack_pixels, render_frame_p2p, render_rays_sharded, shard_bounds  # noqa: E402
 from sinnerf_b200.nerf import Embedding, NeRF  # noqa: E402

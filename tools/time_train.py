@@ -11,7 +11,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from oracle.render_oracle import default_init_params  # noqa: E402  (seeded weights only)
+from sinnerf_b200.synthetic import default_init_params  # noqa: E402  (seeded default-init weights)
 from sinnerf_b200 import synthetic  # noqa: E402
 from sinnerf_b200.nerf import NeRF, Embedding  # noqa: E402
 from sinnerf_b200.rendering import render_rays, render_rays_multi  # noqa: E402
