@@ -1006,6 +1006,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
           tmem_wait_ld();
           trace(tr, tb + 2);
           // bias + activation + hi/lo split, in place: v[2j] = hi pair j, v[2j+1] = lo pair j
+          uint32_t mask_word = 0;        // kTrain == 2: [value > 0] of this thread's 32 columns, stored after the hand-off
           auto finish_group = [&](auto relu_tag, auto sigma_tag) {
             constexpr bool kRelu = decltype(relu_tag)::value, kSigma = decltype(sigma_tag)::value;
             const float2* b2 = reinterpret_cast<const float2*>(bias + c0);
@@ -1028,15 +1029,28 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
                 split_pair_relu<kBf16, kSplit>(x23.x, x23.y, v[2 * j + 2], v[2 * j + 3]);
                 continue;
               }
+              if (kTrain == 2 && !kSigma) {
+                // same sums, one 16-byte bias load and two packed adds per four columns (the training forward's epilogue is
+                // ~2.5x the inference one in instructions -- rn hi words, ReLU mask bits, activation stores -- and sets its pace)
+                const float4 bb = *reinterpret_cast<const float4*>(b2 + j);
+                const float2 x01 = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), make_float2(bb.x, bb.y));
+                const float2 x23 = __fadd2_rn(make_float2(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), make_float2(bb.z, bb.w));
+                x[0] = x01.x; x[1] = x01.y; x[2] = x23.x; x[3] = x23.y;
+                if (kRelu) {
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float2 bb = b2[j + e];
-                x[2 * e] = __uint_as_float(v[2 * (j + e)]) + bb.x;
-                x[2 * e + 1] = __uint_as_float(v[2 * (j + e) + 1]) + bb.y;
-                if (kRelu) { x[2 * e] = fmaxf(x[2 * e], 0.f); x[2 * e + 1] = fmaxf(x[2 * e + 1], 0.f); }
-                if (kSigma) {
-                  const float2 ww = w2[j + e];
-                  sig_part = fmaf(x[2 * e], ww.x, sig_part); sig_part = fmaf(x[2 * e + 1], ww.y, sig_part);
+                  for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const float2 bb = b2[j + e];
+                  x[2 * e] = __uint_as_float(v[2 * (j + e)]) + bb.x;
+                  x[2 * e + 1] = __uint_as_float(v[2 * (j + e) + 1]) + bb.y;
+                  if (kRelu) { x[2 * e] = fmaxf(x[2 * e], 0.f); x[2 * e + 1] = fmaxf(x[2 * e + 1], 0.f); }
+                  if (kSigma) {
+                    const float2 ww = w2[j + e];
+                    sig_part = fmaf(x[2 * e], ww.x, sig_part); sig_part = fmaf(x[2 * e + 1], ww.y, sig_part);
+                  }
                 }
               }
               if (kTrain == 1) {
@@ -1053,15 +1067,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
                 for (int e = 0; e < 4; ++e) mword |= (x[e] > 0.f ? 1u : 0u) << (2 * j + e);
               }
             }
-            if (kTrain == 2 && pt < p.ppad) {
+            if (kTrain == 2 && kBf16 && pt < p.ppad) {
               const bool live = pt < p.n_points;
               unsigned char* hb = p.a_h + (size_t)l * (size_t)p.ppad * (kWidth * 2);
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 *reinterpret_cast<uint4*>(hb + a16_cell(pt, (c0 >> 3) + c, kWidth)) =
                     live ? make_uint4(h16[4 * c], h16[4 * c + 1], h16[4 * c + 2], h16[4 * c + 3]) : make_uint4(0u, 0u, 0u, 0u);
-              p.a_mask[a16_mask_index(l, c0 >> 5, pt, p.ppad)] = live ? mword : 0u;
             }
+            mask_word = mword;
           };
           if (l == 7) finish_group(std::true_type{}, std::true_type{});
           else finish_group(std::true_type{}, std::false_type{});
@@ -1079,6 +1093,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
             tc_fence_before();
             signal(&s.a_ready[h * 2 + q]);
             trace(tr, tb + 3 + q);
+            if (kTrain == 2 && pt < p.ppad) {
+              // what the backward reads -- off the layer-to-layer critical path, after the hand-off.  fp16 modes: the saved
+              // activation IS the hi word just stored to TMEM (rn_fp16 of the saturated value); bf16 modes stored theirs above
+              const bool live = pt < p.n_points;
+              if (!kBf16) {
+                unsigned char* hb = p.a_h + (size_t)l * (size_t)p.ppad * (kWidth * 2);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  *reinterpret_cast<uint4*>(hb + a16_cell(pt, (c0 >> 3) + c, kWidth)) =
+                      live ? make_uint4(phi[4 * c], phi[4 * c + 1], phi[4 * c + 2], phi[4 * c + 3]) : make_uint4(0u, 0u, 0u, 0u);
+              }
+              p.a_mask[a16_mask_index(l, c0 >> 5, pt, p.ppad)] = live ? mask_word : 0u;
+            }
           }
         }
         // ---- background work in the idle window before this layer's next accumulator half is ready
