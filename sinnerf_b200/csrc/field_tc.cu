@@ -1063,10 +1063,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(TcParams p) {
                 // fp16 modes: the hi word of the split IS rn_fp16(value) (saturated); bf16 modes convert separately
                 h16[j] = kBf16 ? pack_half2_sat(x[0], x[1]) : v[2 * j];
                 h16[j + 1] = kBf16 ? pack_half2_sat(x[2], x[3]) : v[2 * j + 2];
+                // [x > 0] of the post-ReLU value (x >= +0; fmaxf(-0, +0) is +0): bits(x) + 0x7fffffff has its top bit set
+                // iff bits(x) != 0, and a funnel shift moves that bit in -- 2 instructions per column instead of 3 (compare,
+                // select, or).  Columns enter in ascending order, so the word is built bit-reversed (one BREV below).
 #pragma unroll
-                for (int e = 0; e < 4; ++e) mword |= (x[e] > 0.f ? 1u : 0u) << (2 * j + e);
+                for (int e = 0; e < 4; ++e) mword = __funnelshift_l(__float_as_uint(x[e]) + 0x7fffffffu, mword, 1);
               }
             }
+            if (kTrain == 2) mword = __brev(mword);
             if (kTrain == 2 && kBf16 && pt < p.ppad) {
               const bool live = pt < p.n_points;
               unsigned char* hb = p.a_h + (size_t)l * (size_t)p.ppad * (kWidth * 2);
